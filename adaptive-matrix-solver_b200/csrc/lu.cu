@@ -1,0 +1,433 @@
+// lu.cu -- batched complex128 LU with partial pivoting for sm_100a (replaces LAPACK zgesv behind AMS:59).
+//
+// Right-looking blocked LU on AUGMENTED systems W_b = [H_b | rhs_b] (column-major, ld = n, n+1 columns): the
+// right-hand side rides along as column n, so after the last step it holds y = L^-1 P rhs and only the
+// back-substitution with U remains; L is never needed again, which is why the row permutation is applied to the
+// columns at and right of the panel only.
+//
+// Per outer step (panel width 128):
+//   lu_panel        one thread-block CLUSTER per candidate (up to 8 CTAs x 512 threads); every thread owns one or
+//                   two rows of the panel and keeps a 16 (8) column inner block of them in registers.  Pivot search
+//                   (BLAS izamax metric |re|+|im|, first maximum) = warp shuffle -> CTA -> cluster reduction through
+//                   distributed shared memory, one cluster barrier per column.  Pivoting is IMPLICIT inside the
+//                   panel (rows are marked, not moved); the net permutation is emitted as <= 256 (dst, src) pairs.
+//   lu_permute_rows applies those pairs to every column >= k0 in one parallel pass (no sequential swap chain).
+//   lu_trtri        inverse of the unit-lower 128 x 128 diagonal block, so that the triangular solve for U12 and the
+//                   trailing update are both plain GEMMs on the FP64 tensor pipe (zgemm.cu).
+#include <cooperative_groups.h>
+#include "lu.cuh"
+#include "../../include/maus_b200.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// H build: fused shift + Psi regulariser (AMS:44-52, 270) while copying the shared matrix into each workspace
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lu_build_aug_kernel(cplx* W, long long strideW, int n, int batch,
+                                                           const cplx* __restrict__ Acm, const cplx* __restrict__ sigma,
+                                                           const double* __restrict__ psi,
+                                                           const unsigned long long* __restrict__ keys,
+                                                           const cplx* __restrict__ R_cm, const cplx* __restrict__ rhs,
+                                                           long long rhs_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= n) return;
+    const long long off = i + (long long)j * n;
+    if (j == n) {
+        for (int b = 0; b < batch; ++b) W[b * strideW + off] = rhs[b * rhs_stride + i];
+        return;
+    }
+    const cplx a = Acm[off];
+    for (int b = 0; b < batch; ++b) {
+        cplx h = a;
+        const double ps = psi[b];
+        if (i == j) { h.x += ps - sigma[b].x; h.y -= sigma[b].y; }
+        if (R_cm) { h.x += R_cm[off].x; h.y += R_cm[off].y; }
+        else if (keys) { cplx r = psi_perturbation(keys[b], (uint32_t)i, (uint32_t)j, ps); h.x += r.x; h.y += r.y; }
+        W[b * strideW + off] = h;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Panel factorisation
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PANEL_NT = 512;
+constexpr int PANEL_MAXC = 8;
+
+template <int IB>
+struct PanelSlot {
+    double val;        // izamax metric of the CTA's best row, -1 when the CTA has no live row
+    int row;           // panel-relative row index
+    int pad;
+    cplx recip;        // 1 / pivot
+    cplx data[IB];     // that row's inner-block entries
+};
+
+template <int R, int IB>
+__global__ void __launch_bounds__(PANEL_NT, 1)
+lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pairs, int* info) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int NC = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / NC;
+    const int T = NC * PANEL_NT;
+    const int tg = rank * PANEL_NT + threadIdx.x;
+    const int m = n - k0;
+    const int ld = n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    cplx* P = W + (long long)b * strideW + (long long)k0 * ld + k0;   // P[r + c*ld]
+
+    __shared__ PanelSlot<IB> slots[2][PANEL_MAXC];
+    __shared__ double wval[PANEL_NT / 32];
+    __shared__ int wrow[PANEL_NT / 32];
+    __shared__ cplx L11[IB][IB + 1];
+    __shared__ cplx U12[IB][LU_NB];
+    __shared__ int piv[LU_NB];
+    __shared__ unsigned char is_piv[LU_NB];
+
+    int row[R];
+    bool valid[R], done[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) { row[q] = tg + q * T; valid[q] = row[q] < m; done[q] = false; }
+    bool zero_seen = false;
+    int zero_col = 0;
+
+    for (int ib0 = 0; ib0 < jb; ib0 += IB) {
+        const int ibw = min(IB, jb - ib0);
+        cplx a[R][IB];
+        bool live[R];     // rows that were not yet pivots when this inner block started
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            live[q] = valid[q] && !done[q];
+#pragma unroll
+            for (int j = 0; j < IB; ++j)
+                a[q][j] = (live[q] && j < ibw) ? P[row[q] + (long long)(ib0 + j) * ld] : cmake(0.0, 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < IB; ++j) {
+            if (j < ibw) {
+                // ---- pivot search: thread -> warp -> CTA -> cluster ----
+                double bv = -1.0; int br = 0x7fffffff;
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (valid[q] && !done[q]) {
+                        double v = cabs1(a[q][j]);
+                        if (v != v) v = INFINITY;
+                        if (v > bv || (v == bv && row[q] < br)) { bv = v; br = row[q]; }
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    int orow = __shfl_xor_sync(0xffffffffu, br, o);
+                    if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; }
+                }
+                if (lane == 0) { wval[warp] = bv; wrow[warp] = br; }
+                __syncthreads();
+                double cv = -1.0; int cr = 0x7fffffff;
+#pragma unroll
+                for (int w = 0; w < PANEL_NT / 32; ++w) {
+                    double ov = wval[w]; int orow = wrow[w];
+                    if (ov > cv || (ov == cv && orow < cr)) { cv = ov; cr = orow; }
+                }
+                // the owner of the CTA's best row publishes it into every CTA's slot[rank]
+                if (cv >= 0.0) {
+#pragma unroll
+                    for (int q = 0; q < R; ++q)
+                        if (valid[q] && !done[q] && row[q] == cr) {
+                            cplx rc = crecip(a[q][j]);
+                            for (int d = 0; d < NC; ++d) {
+                                PanelSlot<IB>* s = cluster.map_shared_rank(&slots[j & 1][rank], d);
+                                s->val = cv; s->row = cr; s->recip = rc;
+#pragma unroll
+                                for (int jj = 0; jj < IB; ++jj) s->data[jj] = a[q][jj];
+                            }
+                        }
+                } else if (threadIdx.x == 0) {
+                    for (int d = 0; d < NC; ++d) {
+                        PanelSlot<IB>* s = cluster.map_shared_rank(&slots[j & 1][rank], d);
+                        s->val = -1.0; s->row = 0x7fffffff;
+                    }
+                }
+                cluster.sync();
+                double wv = -1.0; int wr = 0x7fffffff, wi = 0;
+                for (int d = 0; d < NC; ++d) {
+                    double ov = slots[j & 1][d].val; int orow = slots[j & 1][d].row;
+                    if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wi = d; }
+                }
+                const PanelSlot<IB>& ws = slots[j & 1][wi];
+                if (threadIdx.x < IB) L11[j][threadIdx.x] = ws.data[threadIdx.x];
+                if (threadIdx.x == 0) piv[ib0 + j] = wr;
+                const bool zero = !(wv > 0.0);
+                if (zero && !zero_seen) { zero_seen = true; zero_col = k0 + ib0 + j + 1; }
+                const cplx rc = ws.recip;
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (valid[q] && !done[q]) {
+                        if (row[q] == wr) done[q] = true;
+                        else if (!zero) {
+                            cplx l = cmul(a[q][j], rc);
+                            a[q][j] = l;
+#pragma unroll
+                            for (int jj = j + 1; jj < IB; ++jj) cfms(a[q][jj], l, ws.data[jj]);
+                        }
+                    }
+            }
+        }
+        // write the inner block back (multipliers / U entries stay in their physical rows)
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+            if (live[q])
+#pragma unroll
+                for (int j = 0; j < IB; ++j)
+                    if (j < ibw) P[row[q] + (long long)(ib0 + j) * ld] = a[q][j];
+        __syncthreads();   // L11 / piv complete in this CTA
+        const int rest = jb - (ib0 + ibw);
+        if (rest > 0) {
+            // (i) U12 block = L11^-1 * (pivot rows, remaining panel columns); every CTA computes its own copy
+            if ((int)threadIdx.x < rest) {
+                const int c = threadIdx.x;
+                const long long coff = (long long)(ib0 + ibw + c) * ld;
+                for (int j = 0; j < ibw; ++j) {
+                    cplx x = __ldcg(&P[piv[ib0 + j] + coff]);
+                    for (int i = 0; i < j; ++i) cfms(x, L11[j][i], U12[i][c]);
+                    U12[j][c] = x;
+                }
+            }
+            cluster.sync();   // every CTA has read the pivot rows before rank 0 overwrites them with U12
+            if (rank == 0 && (int)threadIdx.x < rest) {
+                const long long coff = (long long)(ib0 + ibw + threadIdx.x) * ld;
+                for (int j = 0; j < ibw; ++j) P[piv[ib0 + j] + coff] = U12[j][threadIdx.x];
+            }
+            // (ii) rank-ibw update of the remaining panel columns for the rows that are still live
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                if (valid[q] && !done[q]) {
+                    cplx* prow = P + row[q] + (long long)(ib0 + ibw) * ld;
+                    for (int c = 0; c < rest; ++c) {
+                        cplx x = prow[(long long)c * ld];
+#pragma unroll
+                        for (int j = 0; j < IB; ++j)
+                            if (j < ibw) cfms(x, a[q][j], U12[j][c]);
+                        prow[(long long)c * ld] = x;
+                    }
+                }
+        }
+        // Updates written in (ii) are read by other CTAs in the next block's step (i): the column loop of the next
+        // block contains at least one cluster barrier (release/acquire) before that read, and the reads use ld.cg.
+    }
+    __syncthreads();
+    // ---- net row permutation of this panel (relative to k0) ----
+    if (rank == 0) {
+        if (threadIdx.x < LU_NB) is_piv[threadIdx.x] = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < jb && piv[threadIdx.x] < jb) is_piv[piv[threadIdx.x]] = 1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            LuPairs* pr = pairs + b;
+            int cnt = 0, d = 0;   // d walks the non-pivot rows of the top block in increasing order
+            for (int j = 0; j < jb; ++j) {
+                const int pj = piv[j];
+                if (pj != j) { pr->dst[cnt] = j; pr->src[cnt] = pj; ++cnt; }
+                if (pj >= jb) {
+                    while (is_piv[d]) ++d;
+                    pr->dst[cnt] = pj; pr->src[cnt] = d; ++cnt; ++d;
+                }
+            }
+            pr->count = cnt;
+            if (zero_seen && info[b] == 0) info[b] = zero_col;
+        }
+    }
+    cluster.sync();   // no CTA may exit while a peer could still address its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Row permutation of all columns >= k0
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PERM_COLS = 8;
+__global__ void __launch_bounds__(256) lu_permute_rows_kernel(cplx* W, long long strideW, int n, int k0,
+                                                              const LuPairs* __restrict__ pairs) {
+    __shared__ cplx tmp[LU_MAX_PAIRS * PERM_COLS];
+    __shared__ int sdst[LU_MAX_PAIRS], ssrc[LU_MAX_PAIRS];
+    const int b = blockIdx.y;
+    const int cnt = pairs[b].count;
+    if (cnt == 0) return;
+    for (int q = threadIdx.x; q < cnt; q += blockDim.x) { sdst[q] = pairs[b].dst[q]; ssrc[q] = pairs[b].src[q]; }
+    __syncthreads();
+    const int col0 = k0 + blockIdx.x * PERM_COLS;
+    const int ncol = min(PERM_COLS, n + 1 - col0);
+    cplx* Wb = W + (long long)b * strideW + k0;
+    const int total = cnt * ncol;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int c = idx / cnt, q = idx - c * cnt;
+        tmp[idx] = Wb[ssrc[q] + (long long)(col0 + c) * n];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int c = idx / cnt, q = idx - c * cnt;
+        Wb[sdst[q] + (long long)(col0 + c) * n] = tmp[idx];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Inverse of the unit-lower-triangular diagonal block
+// ------------------------------------------------------------------------------------------------------------
+// thread c owns column c of X = L11^-1; X is kept packed (row p holds columns 0..p) in shared memory.
+__global__ void __launch_bounds__(LU_NB) lu_trtri_kernel(const cplx* __restrict__ W, long long strideW, int n, int k0,
+                                                         int jb, cplx* __restrict__ Linv) {
+    extern __shared__ __align__(16) unsigned char trtri_smem[];
+    cplx* X = reinterpret_cast<cplx*>(trtri_smem);                 // jb*(jb+1)/2
+    cplx* rowbuf = X + (LU_NB * (LU_NB + 1)) / 2;                  // 2 x LU_NB (double buffered row of L)
+    const int b = blockIdx.x, c = threadIdx.x;
+    const cplx* L = W + (long long)b * strideW + (long long)k0 * n + k0;   // L[r + p*n]
+    if (c < jb) X[(c * (c + 1)) / 2 + c] = cmake(1.0, 0.0);
+    if (jb > 1 && c < 1) rowbuf[c] = L[1 + (long long)c * n];
+    __syncthreads();
+    for (int r = 1; r < jb; ++r) {
+        const cplx* lr = rowbuf + (r & 1) * LU_NB;
+        if (r + 1 < jb && c < r + 1) rowbuf[((r + 1) & 1) * LU_NB + c] = L[(r + 1) + (long long)c * n];   // prefetch next row
+        if (c < r) {
+            cplx acc = cmake(0.0, 0.0);
+            for (int p = c; p < r; ++p) cfms(acc, lr[p], X[(p * (p + 1)) / 2 + c]);
+            X[(r * (r + 1)) / 2 + c] = acc;
+        }
+        __syncthreads();
+    }
+    cplx* out = Linv + (long long)b * LU_NB * LU_NB;
+    for (int r = 0; r < jb; ++r)
+        if (c < jb) out[r + c * LU_NB] = (c <= r) ? X[(r * (r + 1)) / 2 + c] : cmake(0.0, 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Back substitution with U (one CTA per candidate; the right-hand side lives in shared memory)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BS_NT = 512;
+constexpr int BS_BLK = 32;
+__global__ void __launch_bounds__(BS_NT) lu_backsolve_kernel(const cplx* __restrict__ W, long long strideW, int n,
+                                                             const int* __restrict__ info, cplx* __restrict__ X,
+                                                             int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char bs_smem[];
+    cplx* y = reinterpret_cast<cplx*>(bs_smem);          // n
+    cplx* D = y + n;                                     // BS_BLK x (BS_BLK+1)
+    __shared__ int bad;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const cplx* Wb = W + (long long)b * strideW;
+    for (int i = tid; i < n; i += BS_NT) y[i] = Wb[i + (long long)n * n];
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    const int nblk = (n + BS_BLK - 1) / BS_BLK;
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int r0 = kb * BS_BLK, bs = min(BS_BLK, n - r0);
+        for (int idx = tid; idx < bs * bs; idx += BS_NT) {
+            int i = idx % bs, j = idx / bs;
+            D[i * (BS_BLK + 1) + j] = Wb[(r0 + i) + (long long)(r0 + j) * n];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            cplx yi = (lane < bs) ? y[r0 + lane] : cmake(0.0, 0.0);
+            for (int j = bs - 1; j >= 0; --j) {
+                cplx yj = cmake(__shfl_sync(0xffffffffu, yi.x, j), __shfl_sync(0xffffffffu, yi.y, j));
+                cplx xj = cdiv(yj, D[j * (BS_BLK + 1) + j]);
+                if (lane == j) yi = xj;
+                else if (lane < j) cfms(yi, D[lane * (BS_BLK + 1) + j], xj);
+            }
+            if (lane < bs) y[r0 + lane] = yi;
+        }
+        __syncthreads();
+        for (int i = tid; i < r0; i += BS_NT) {
+            cplx acc = y[i];
+            const cplx* u = Wb + i + (long long)r0 * n;
+#pragma unroll 8
+            for (int j = 0; j < bs; ++j) cfms(acc, __ldg(&u[(long long)j * n]), y[r0 + j]);
+            y[i] = acc;
+        }
+        __syncthreads();
+    }
+    int mybad = 0;
+    for (int i = tid; i < n; i += BS_NT) {
+        cplx v = y[i];
+        if (!cfinite(v)) mybad = 1;
+        X[(long long)b * n + i] = v;
+    }
+    if (mybad) bad = 1;
+    __syncthreads();
+    if (tid == 0) {
+        if (status[b] == 0) {
+            if (info[b] != 0) status[b] = MAUS_ST_ZERO_PIVOT;
+            else if (bad) status[b] = MAUS_ST_NONFINITE;
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+cudaError_t lu_build_aug(cplx* W, long long strideW, int n, int batch, const cplx* Acm, const cplx* sigma,
+                         const double* psi, const unsigned long long* keys, const cplx* R_cm, const cplx* rhs,
+                         long long rhs_stride, cudaStream_t stream) {
+    dim3 grid((n + 255) / 256, n + 1, 1);
+    lu_build_aug_kernel<<<grid, 256, 0, stream>>>(W, strideW, n, batch, Acm, sigma, psi, keys, R_cm, rhs, rhs_stride);
+    return cudaGetLastError();
+}
+
+template <int R, int IB>
+static cudaError_t launch_panel(cplx* W, long long strideW, int n, int k0, int jb, int batch, LuPairs* pairs, int* info,
+                                int nc, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(batch * nc, 1, 1);
+    cfg.blockDim = dim3(PANEL_NT, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, lu_panel_kernel<R, IB>, W, strideW, n, k0, jb, pairs, info);
+}
+
+cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batch, LuPairs* pairs, int* info,
+                     cudaStream_t stream) {
+    const int m = n - k0;
+    if (m > LU_MAX_N) return cudaErrorInvalidValue;
+    int R = (m > PANEL_MAXC * PANEL_NT) ? 2 : 1;
+    int need = (m + R * PANEL_NT - 1) / (R * PANEL_NT);
+    int nc = 1;
+    while (nc < need) nc <<= 1;
+    if (R == 1) return launch_panel<1, 16>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+    return launch_panel<2, 8>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+}
+
+cudaError_t lu_permute_rows(cplx* W, long long strideW, int n, int k0, int batch, const LuPairs* pairs,
+                            cudaStream_t stream) {
+    const int ncols = n + 1 - k0;
+    dim3 grid((ncols + PERM_COLS - 1) / PERM_COLS, batch, 1);
+    lu_permute_rows_kernel<<<grid, 256, 0, stream>>>(W, strideW, n, k0, pairs);
+    return cudaGetLastError();
+}
+
+cudaError_t lu_trtri(const cplx* W, long long strideW, int n, int k0, int jb, int batch, cplx* Linv, cudaStream_t stream) {
+    const size_t smem = ((size_t)(LU_NB * (LU_NB + 1)) / 2 + 2 * LU_NB) * sizeof(cplx);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(lu_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    lu_trtri_kernel<<<batch, LU_NB, smem, stream>>>(W, strideW, n, k0, jb, Linv);
+    return cudaGetLastError();
+}
+
+cudaError_t lu_backsolve(const cplx* W, long long strideW, int n, int batch, const int* info, cplx* X, int* status,
+                         cudaStream_t stream) {
+    const size_t smem = ((size_t)n + BS_BLK * (BS_BLK + 1)) * sizeof(cplx);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(lu_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem = smem;
+    }
+    lu_backsolve_kernel<<<batch, BS_NT, smem, stream>>>(W, strideW, n, info, X, status);
+    return cudaGetLastError();
+}

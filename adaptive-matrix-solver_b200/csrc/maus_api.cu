@@ -1,0 +1,690 @@
+// maus_api.cu -- C ABI of libmaus_b200.so (see include/maus_b200.h for the contract and reference citations).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <algorithm>
+#include "ctx.cuh"
+#include "vec.cuh"
+#include "spmv.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------------------
+int maus_fail(maus_ctx* ctx, int code, const char* what, cudaError_t e) {
+    if (ctx) {
+        char buf[512];
+        if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(buf, sizeof buf, "%s", what);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+cudaError_t maus_dev_alloc(maus_ctx* ctx, void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e == cudaSuccess) ctx->bytes_held += (long long)bytes;
+    return e;
+}
+void maus_dev_free(maus_ctx* ctx, void* p, size_t bytes) {
+    if (p) { cudaFree(p); ctx->bytes_held -= (long long)bytes; }
+}
+
+int prof_begin(maus_ctx* ctx, int kind, double work) {
+    ProfAccum& pr = ctx->prof;
+    if (!pr.enabled) return -1;
+    if (pr.used + 2 > pr.ev.size()) {
+        // drain: accumulate what is recorded so far
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t i = 0; i + 1 < pr.used; i += 2) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pr.ev[i], pr.ev[i + 1]);
+            pr.ms[pr.kind[i / 2]] += ms;
+        }
+        pr.used = 0;
+        if (pr.ev.empty()) {
+            pr.ev.resize(4096); pr.kind.resize(2048);
+            for (auto& e : pr.ev) cudaEventCreate(&e);
+        }
+    }
+    int h = (int)pr.used;
+    pr.kind[h / 2] = kind;
+    pr.launches[kind] += 1;
+    pr.work[kind] += work;
+    cudaEventRecord(pr.ev[h], ctx->stream);
+    pr.used += 2;
+    return h;
+}
+void prof_end(maus_ctx* ctx, int h) {
+    if (h < 0) return;
+    cudaEventRecord(ctx->prof.ev[h + 1], ctx->stream);
+}
+
+template <typename T>
+static int ensure(maus_ctx* ctx, T** p, long long count) {
+    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)p, (size_t)count * sizeof(T)));
+    return MAUS_OK;
+}
+
+static void free_population(maus_ctx* ctx) {
+    const long long n = ctx->n, C = ctx->Ccap;
+    maus_dev_free(ctx, ctx->V, n * C * sizeof(cplx)); maus_dev_free(ctx, ctx->X, n * C * sizeof(cplx));
+    maus_dev_free(ctx, ctx->Y, n * C * sizeof(cplx));
+    maus_dev_free(ctx, ctx->lambda, C * sizeof(cplx)); maus_dev_free(ctx, ctx->sigma, C * sizeof(cplx));
+    maus_dev_free(ctx, ctx->psi, C * 8); maus_dev_free(ctx, ctx->alpha, C * 8); maus_dev_free(ctx, ctx->vnorm2, C * 8);
+    maus_dev_free(ctx, ctx->resid, C * 8); maus_dev_free(ctx, ctx->mixnorm, C * 8); maus_dev_free(ctx, ctx->keys, C * 8);
+    maus_dev_free(ctx, ctx->status, C * 4); maus_dev_free(ctx, ctx->iters, C * 4); maus_dev_free(ctx, ctx->info, C * 4);
+    maus_dev_free(ctx, ctx->skip, C); maus_dev_free(ctx, ctx->jac, C);
+    ctx->V = ctx->X = ctx->Y = nullptr; ctx->lambda = ctx->sigma = nullptr;
+    ctx->psi = ctx->alpha = ctx->vnorm2 = ctx->resid = ctx->mixnorm = nullptr; ctx->keys = nullptr;
+    ctx->status = ctx->iters = ctx->info = nullptr; ctx->skip = ctx->jac = nullptr;
+    ctx->Ccap = 0;
+}
+
+int maus_ensure_population(maus_ctx* ctx, long long C) {
+    if (ctx->n <= 0) return maus_fail(ctx, MAUS_E_STATE, "matrix not set");
+    if (C <= ctx->Ccap) return MAUS_OK;
+    // grow; the resident vectors survive
+    const long long n = ctx->n, oldC = ctx->Ccap;
+    cplx* oldV = ctx->V;
+    ctx->V = nullptr;                      // detach so free_population leaves it alone
+    if (oldV) ctx->bytes_held += 0;
+    free_population(ctx);
+    const long long cap = std::max<long long>(C, 8);
+    int rc;
+    if ((rc = ensure(ctx, &ctx->V, n * cap))) return rc;
+    if (oldV) {
+        MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->V, oldV, (size_t)n * oldC * sizeof(cplx), cudaMemcpyDeviceToDevice, ctx->stream));
+        MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        maus_dev_free(ctx, oldV, n * oldC * sizeof(cplx));
+    }
+    if ((rc = ensure(ctx, &ctx->X, n * cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->Y, n * cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->lambda, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->sigma, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->psi, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->alpha, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->vnorm2, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->resid, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->mixnorm, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->keys, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->status, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->iters, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->info, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->skip, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->jac, cap))) return rc;
+    ctx->Ccap = cap;
+    return MAUS_OK;
+}
+
+static void free_slot(maus_ctx* ctx, MatrixSlot& s, long long n) {
+    maus_dev_free(ctx, s.rm, n * n * sizeof(cplx)); maus_dev_free(ctx, s.cm, n * n * sizeof(cplx));
+    maus_dev_free(ctx, s.rowptr, (n + 1) * 8); maus_dev_free(ctx, s.colidx, s.nnz * 4);
+    maus_dev_free(ctx, s.vals, s.nnz * sizeof(cplx)); maus_dev_free(ctx, s.diag, n * sizeof(cplx));
+    s = MatrixSlot();
+}
+
+static void free_lu(maus_ctx* ctx) {
+    maus_dev_free(ctx, ctx->W, ctx->Wbytes);
+    maus_dev_free(ctx, ctx->pairs, (size_t)ctx->Wbatch * sizeof(LuPairs));
+    maus_dev_free(ctx, ctx->Linv, (size_t)ctx->Wbatch * LU_NB * LU_NB * sizeof(cplx));
+    ctx->W = nullptr; ctx->pairs = nullptr; ctx->Linv = nullptr; ctx->Wbytes = 0; ctx->Wbatch = 0;
+}
+
+// set a new problem size: drops everything that depends on n
+static int reset_for_n(maus_ctx* ctx, long long n) {
+    if (ctx->n == n) return MAUS_OK;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->n > 0) {
+        free_population(ctx);
+        free_slot(ctx, ctx->slot[0], ctx->n); free_slot(ctx, ctx->slot[1], ctx->n);
+        maus_dev_free(ctx, ctx->b, ctx->n * sizeof(cplx)); ctx->b = nullptr; ctx->b_set = false;
+        maus_dev_free(ctx, ctx->Rcm, ctx->n * ctx->n * sizeof(cplx)); ctx->Rcm = nullptr;
+        free_lu(ctx);
+        maus_gmres_free(ctx);
+        ctx->slot1_set = false;
+    }
+    ctx->n = n;
+    return MAUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int maus_create(maus_ctx** out, int device) {
+    if (!out) return MAUS_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return MAUS_E_CUDA;   // no CPU fallback
+    maus_ctx* ctx = new (std::nothrow) maus_ctx();
+    if (!ctx) return MAUS_E_NOMEM;
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { delete ctx; return MAUS_E_CUDA; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return MAUS_E_CUDA; }
+    if (prop.major != 10) { delete ctx; return MAUS_E_CUDA; }   // sm_100a only
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return MAUS_E_CUDA; }
+    *out = ctx;
+    return MAUS_OK;
+}
+
+extern "C" int maus_destroy(maus_ctx* ctx) {
+    if (!ctx) return MAUS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    reset_for_n(ctx, 0);
+    for (auto& e : ctx->prof.ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MAUS_OK;
+}
+
+extern "C" const char* maus_last_error(maus_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int maus_set_workspace_limit(maus_ctx* ctx, int64_t bytes) {
+    if (!ctx || bytes < 0) return MAUS_E_ARG;
+    ctx->ws_limit = bytes;
+    return MAUS_OK;
+}
+
+extern "C" int maus_info(maus_ctx* ctx, int* device, int* sm_count, int64_t* bytes_held) {
+    if (!ctx) return MAUS_E_ARG;
+    if (device) *device = ctx->device;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (bytes_held) *bytes_held = ctx->bytes_held;
+    return MAUS_OK;
+}
+
+extern "C" void* maus_stream(maus_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int64_t maus_launch_count(maus_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void* maus_alloc_pinned(int64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void maus_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int maus_profile_reset(maus_ctx* ctx, int enable) {
+    if (!ctx) return MAUS_E_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    ProfAccum& pr = ctx->prof;
+    pr.enabled = enable != 0;
+    pr.used = 0;
+    pr.ms[0] = pr.ms[1] = 0.0; pr.launches[0] = pr.launches[1] = 0; pr.work[0] = pr.work[1] = 0.0;
+    return MAUS_OK;
+}
+
+extern "C" int maus_profile_read(maus_ctx* ctx, double* lu_gemm_ms, int64_t* lu_gemm_launches, double* lu_gemm_flops,
+                                 double* matvec_ms, int64_t* matvec_launches, double* matvec_bytes) {
+    if (!ctx) return MAUS_E_ARG;
+    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ProfAccum& pr = ctx->prof;
+    for (size_t i = 0; i + 1 < pr.used; i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pr.ev[i], pr.ev[i + 1]);
+        pr.ms[pr.kind[i / 2]] += ms;
+    }
+    pr.used = 0;
+    if (lu_gemm_ms) *lu_gemm_ms = pr.ms[0];
+    if (lu_gemm_launches) *lu_gemm_launches = pr.launches[0];
+    if (lu_gemm_flops) *lu_gemm_flops = pr.work[0];
+    if (matvec_ms) *matvec_ms = pr.ms[1];
+    if (matvec_launches) *matvec_launches = pr.launches[1];
+    if (matvec_bytes) *matvec_bytes = pr.work[1];
+    return MAUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// problem upload
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int maus_set_dense(maus_ctx* ctx, int slot, int64_t n, const double* A_rowmajor) {
+    if (!ctx || !A_rowmajor || n <= 0 || slot < 0 || slot > 1) return maus_fail(ctx, MAUS_E_ARG, "maus_set_dense: bad argument");
+    if (n > 0x7fffffffLL) return maus_fail(ctx, MAUS_E_ARG, "maus_set_dense: n too large");
+    cudaSetDevice(ctx->device);
+    if (slot == 1 && ctx->n != n) return maus_fail(ctx, MAUS_E_STATE, "maus_set_dense: set slot 0 first");
+    if (slot == 0) { int rc = reset_for_n(ctx, n); if (rc) return rc; }
+    MatrixSlot& s = ctx->slot[slot];
+    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (s.sparse) free_slot(ctx, s, n);
+    const size_t bytes = (size_t)n * n * sizeof(cplx);
+    if (!s.rm) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.rm, bytes));
+    if (!s.cm) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.cm, bytes));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(s.rm, A_rowmajor, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MAUS_CUDA(ctx, vec_rowmajor_to_colmajor(s.rm, s.cm, (int)n, ctx->stream));
+    ctx->launches += 1;
+    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    s.dense = true;
+    if (slot == 1) ctx->slot1_set = true;
+    return MAUS_OK;
+}
+
+extern "C" int maus_set_csc(maus_ctx* ctx, int slot, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowidx,
+                            const double* vals) {
+    if (!ctx || !colptr || (nnz > 0 && (!rowidx || !vals)) || n <= 0 || nnz < 0 || slot < 0 || slot > 1)
+        return maus_fail(ctx, MAUS_E_ARG, "maus_set_csc: bad argument");
+    if (n > 0x7fffffffLL) return maus_fail(ctx, MAUS_E_ARG, "maus_set_csc: n too large");
+    cudaSetDevice(ctx->device);
+    if (slot == 1 && ctx->n != n) return maus_fail(ctx, MAUS_E_STATE, "maus_set_csc: set slot 0 first");
+    if (slot == 0) { int rc = reset_for_n(ctx, n); if (rc) return rc; }
+    MatrixSlot& s = ctx->slot[slot];
+    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_slot(ctx, s, n);
+    // CSC -> CSR on the host (one-time O(nnz) counting sort; duplicates are summed like scipy's tocsr + sum_duplicates
+    // is NOT needed: entries are kept as-is, the matvec adds them)
+    std::vector<long long> rowptr((size_t)n + 1, 0);
+    for (long long k = 0; k < nnz; ++k) {
+        long long r = rowidx[k];
+        if (r < 0 || r >= n) return maus_fail(ctx, MAUS_E_ARG, "maus_set_csc: row index out of range");
+        rowptr[(size_t)r + 1]++;
+    }
+    for (long long i = 0; i < n; ++i) rowptr[(size_t)i + 1] += rowptr[(size_t)i];
+    std::vector<int> colidx((size_t)nnz);
+    std::vector<cplx> v((size_t)nnz);
+    std::vector<cplx> diag((size_t)n, cmake(0.0, 0.0));
+    std::vector<long long> fill(rowptr.begin(), rowptr.end() - 1);
+    double amax = 0.0;
+    for (long long j = 0; j < n; ++j) {
+        if (colptr[j] > colptr[j + 1] || colptr[j + 1] > nnz) return maus_fail(ctx, MAUS_E_ARG, "maus_set_csc: bad colptr");
+        for (long long k = colptr[j]; k < colptr[j + 1]; ++k) {
+            long long r = rowidx[k];
+            long long p = fill[(size_t)r]++;
+            colidx[(size_t)p] = (int)j;
+            cplx z = cmake(vals[2 * k], vals[2 * k + 1]);
+            v[(size_t)p] = z;
+            if (r == j) { diag[(size_t)r].x += z.x; diag[(size_t)r].y += z.y; }
+            amax = std::max(amax, std::fabs(z.x) + std::fabs(z.y));
+        }
+    }
+    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.rowptr, (size_t)(n + 1) * 8));
+    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.colidx, (size_t)nnz * 4));
+    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.vals, (size_t)nnz * sizeof(cplx)));
+    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.diag, (size_t)n * sizeof(cplx)));
+    s.nnz = nnz;
+    MAUS_CUDA(ctx, cudaMemcpy(s.rowptr, rowptr.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice));
+    if (nnz) {
+        MAUS_CUDA(ctx, cudaMemcpy(s.colidx, colidx.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice));
+        MAUS_CUDA(ctx, cudaMemcpy(s.vals, v.data(), (size_t)nnz * sizeof(cplx), cudaMemcpyHostToDevice));
+    }
+    MAUS_CUDA(ctx, cudaMemcpy(s.diag, diag.data(), (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice));
+    s.amax = amax;
+    s.sparse = true;
+    if (slot == 1) ctx->slot1_set = true;
+    return MAUS_OK;
+}
+
+extern "C" int maus_set_rhs(maus_ctx* ctx, const double* b) {
+    if (!ctx || !b) return maus_fail(ctx, MAUS_E_ARG, "maus_set_rhs: bad argument");
+    if (ctx->n <= 0) return maus_fail(ctx, MAUS_E_STATE, "maus_set_rhs: matrix not set");
+    cudaSetDevice(ctx->device);
+    if (!ctx->b) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&ctx->b, (size_t)ctx->n * sizeof(cplx)));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->b, b, (size_t)ctx->n * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->b_set = true;
+    return MAUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// resident vectors
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int maus_upload_vectors(maus_ctx* ctx, int64_t C, const double* V) {
+    if (!ctx || !V || C <= 0) return maus_fail(ctx, MAUS_E_ARG, "maus_upload_vectors: bad argument");
+    cudaSetDevice(ctx->device);
+    int rc = maus_ensure_population(ctx, C); if (rc) return rc;
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->V, V, (size_t)C * ctx->n * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MAUS_OK;
+}
+extern "C" int maus_download_vectors(maus_ctx* ctx, int64_t C, double* V) {
+    if (!ctx || !V || C <= 0 || C > ctx->Ccap) return maus_fail(ctx, MAUS_E_ARG, "maus_download_vectors: bad argument");
+    cudaSetDevice(ctx->device);
+    MAUS_CUDA(ctx, cudaMemcpyAsync(V, ctx->V, (size_t)C * ctx->n * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MAUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// matrix application
+// ------------------------------------------------------------------------------------------------------------
+int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, cplx* Y, long long C) {
+    if (slot == 1 && !ctx->slot1_set) slot = 0;
+    MatrixSlot& s = ctx->slot[slot];
+    const long long n = ctx->n;
+    if (s.dense) {
+        if (C <= 8) {
+            int h = prof_begin(ctx, 1, (double)((C + 3) / 4) * 16.0 * n * n + 32.0 * n * C);
+            MAUS_CUDA(ctx, vec_gemv_rowmajor(s.rm, V, Y, (int)n, (int)C, ctx->stream));
+            prof_end(ctx, h);
+            ctx->launches += (C + 3) / 4;
+        } else {
+            ZgemmParams p;
+            p.A = s.cm; p.lda = n; p.strideA = 0;
+            p.B = V; p.ldb = n; p.strideB = 0;
+            p.C = Y; p.ldc = n; p.strideC = 0;
+            p.M = (int)n; p.N = (int)C; p.K = (int)n; p.batch = 1; p.beta = 0; p.negate = 0;
+            MAUS_CUDA(ctx, zgemm_dmma_launch(p, ctx->stream));
+            ctx->launches += 1;
+        }
+        return MAUS_OK;
+    }
+    if (s.sparse) {
+        int h = prof_begin(ctx, 1, (double)((C + 3) / 4) * (20.0 * s.nnz + 8.0 * (n + 1)) + 32.0 * n * C);
+        MAUS_CUDA(ctx, csr_spmm(s.rowptr, s.colidx, s.vals, V, Y, n, (int)C, ctx->stream));
+        prof_end(ctx, h);
+        ctx->launches += (C + 3) / 4;
+        return MAUS_OK;
+    }
+    return maus_fail(ctx, MAUS_E_STATE, "matrix slot not set");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// batched LU solve
+// ------------------------------------------------------------------------------------------------------------
+static int ensure_lu_workspace(maus_ctx* ctx, long long C, int* batch_out) {
+    const long long n = ctx->n;
+    const long long per = (long long)n * (n + 1) * (long long)sizeof(cplx);
+    if (ctx->Wbatch >= C) { *batch_out = ctx->Wbatch; return MAUS_OK; }
+    size_t free_b = 0, total_b = 0;
+    MAUS_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    long long budget = (long long)((double)(free_b + (size_t)ctx->Wbytes) * 0.6);
+    if (ctx->ws_limit > 0) budget = std::min<long long>(budget, ctx->ws_limit);
+    long long fit = budget / (per + (long long)sizeof(LuPairs) + (long long)LU_NB * LU_NB * sizeof(cplx));
+    if (fit < 1) return maus_fail(ctx, MAUS_E_NOMEM, "LU workspace does not fit on the device");
+    long long want = std::min<long long>(C, fit);
+    if (want <= ctx->Wbatch) { *batch_out = ctx->Wbatch; return MAUS_OK; }
+    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_lu(ctx);
+    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&ctx->W, (size_t)(want * per)));
+    ctx->Wbytes = want * per;
+    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&ctx->pairs, (size_t)want * sizeof(LuPairs)));
+    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&ctx->Linv, (size_t)want * LU_NB * LU_NB * sizeof(cplx)));
+    ctx->Wbatch = (int)want;
+    *batch_out = (int)want;
+    return MAUS_OK;
+}
+
+int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* psi, const unsigned long long* keys,
+                  const cplx* Rcm, const cplx* rhs, long long rhs_stride, cplx* X, int* status) {
+    MatrixSlot& s = ctx->slot[0];
+    if (!s.dense) return maus_fail(ctx, MAUS_E_ARG, "direct (LU) solve needs a dense matrix; sparse problems use GMRES");
+    const int n = (int)ctx->n;
+    if (n > LU_MAX_N) return maus_fail(ctx, MAUS_E_ARG, "direct (LU) solve supports n <= 8192");
+    int wb = 0;
+    int rc = ensure_lu_workspace(ctx, C, &wb); if (rc) return rc;
+    const long long strideW = (long long)n * (n + 1);
+    cudaStream_t st = ctx->stream;
+    for (long long c0 = 0; c0 < C; c0 += wb) {
+        const int nb = (int)std::min<long long>(wb, C - c0);
+        MAUS_CUDA(ctx, lu_build_aug(ctx->W, strideW, n, nb, s.cm, sigma + c0, psi + c0, keys ? keys + c0 : nullptr, Rcm,
+                                    rhs + c0 * rhs_stride, rhs_stride, st));
+        MAUS_CUDA(ctx, cudaMemsetAsync(ctx->info, 0, (size_t)nb * sizeof(int), st));
+        ctx->launches += 1;
+        for (int k0 = 0; k0 < n; k0 += LU_NB) {
+            const int jb = std::min(LU_NB, n - k0);
+            MAUS_CUDA(ctx, lu_panel(ctx->W, strideW, n, k0, jb, nb, ctx->pairs, ctx->info, st));
+            MAUS_CUDA(ctx, lu_permute_rows(ctx->W, strideW, n, k0, nb, ctx->pairs, st));
+            ctx->launches += 2;
+            const int ncols = n + 1 - (k0 + jb);       // trailing columns incl. the rhs column
+            if (ncols <= 0) continue;
+            MAUS_CUDA(ctx, lu_trtri(ctx->W, strideW, n, k0, jb, nb, ctx->Linv, st));
+            ZgemmParams p;
+            cplx* A12 = ctx->W + (long long)(k0 + jb) * n + k0;
+            p.A = ctx->Linv; p.lda = LU_NB; p.strideA = (long long)LU_NB * LU_NB;
+            p.B = A12; p.ldb = n; p.strideB = strideW;
+            p.C = A12; p.ldc = n; p.strideC = strideW;
+            p.M = jb; p.N = ncols; p.K = jb; p.batch = nb; p.beta = 0; p.negate = 0;
+            int h = prof_begin(ctx, 0, 8.0 * jb * (double)ncols * jb * nb);
+            MAUS_CUDA(ctx, zgemm_dmma_launch(p, st));            // U12 = L11^-1 A12 (in place, one row tile)
+            prof_end(ctx, h);
+            ctx->launches += 2;
+            const int m2 = n - k0 - jb;
+            if (m2 > 0) {
+                p.A = ctx->W + (long long)k0 * n + (k0 + jb); p.lda = n; p.strideA = strideW;        // L21
+                p.B = A12;                                                                           // U12
+                p.C = ctx->W + (long long)(k0 + jb) * n + (k0 + jb);                                 // A22
+                p.M = m2; p.N = ncols; p.K = jb; p.beta = 1; p.negate = 1;
+                h = prof_begin(ctx, 0, 8.0 * m2 * (double)ncols * jb * nb);
+                MAUS_CUDA(ctx, zgemm_dmma_launch(p, st));
+                prof_end(ctx, h);
+                ctx->launches += 1;
+            }
+        }
+        MAUS_CUDA(ctx, lu_backsolve(ctx->W, strideW, n, nb, ctx->info, X + c0 * n, status + c0, st));
+        ctx->launches += 1;
+    }
+    return MAUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// granular entry points
+// ------------------------------------------------------------------------------------------------------------
+static int check_ready(maus_ctx* ctx, int64_t C, const char* who) {
+    if (!ctx) return MAUS_E_ARG;
+    if (C <= 0) return maus_fail(ctx, MAUS_E_ARG, who);
+    if (ctx->n <= 0 || !(ctx->slot[0].dense || ctx->slot[0].sparse)) return maus_fail(ctx, MAUS_E_STATE, "matrix not set");
+    cudaSetDevice(ctx->device);
+    return maus_ensure_population(ctx, C);
+}
+
+extern "C" int maus_rq(maus_ctx* ctx, int64_t C, const double* V, double* lambda_out, double* vnorm2_out) {
+    int rc = check_ready(ctx, C, "maus_rq: bad C"); if (rc) return rc;
+    const long long n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    if (V) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->V, V, (size_t)C * n * sizeof(cplx), cudaMemcpyHostToDevice, st));
+    if ((rc = maus_apply_matrix(ctx, 0, ctx->V, ctx->Y, C))) return rc;
+    MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, nullptr, st));
+    ctx->launches += 1;
+    if (lambda_out) MAUS_CUDA(ctx, cudaMemcpyAsync(lambda_out, ctx->lambda, (size_t)C * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    if (vnorm2_out) MAUS_CUDA(ctx, cudaMemcpyAsync(vnorm2_out, ctx->vnorm2, (size_t)C * 8, cudaMemcpyDeviceToHost, st));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(st));
+    return MAUS_OK;
+}
+
+static int solve_device(maus_ctx* ctx, long long C, int method, const cplx* rhs, long long rhs_stride, const cplx* Rcm,
+                        bool have_keys) {
+    const unsigned long long* keys = have_keys ? ctx->keys : nullptr;   // no key = no random perturbation (sparse, AMS:47)
+    // sigma / psi / keys / jac already on the device; status pre-set (0 = solve, non-zero = skip handled by caller)
+    if (method == MAUS_METHOD_LU)
+        return maus_lu_solve(ctx, C, ctx->sigma, ctx->psi, keys, Rcm, rhs, rhs_stride, ctx->X, ctx->status);
+    if (method == MAUS_METHOD_GMRES)
+        return maus_gmres_solve(ctx, C, ctx->sigma, ctx->psi, keys, ctx->jac, rhs, rhs_stride, ctx->X, ctx->status,
+                                ctx->iters);
+    return maus_fail(ctx, MAUS_E_ARG, "unknown solver method");
+}
+
+extern "C" int maus_solve_shifted(maus_ctx* ctx, int64_t C, const double* sigma, const double* psi, const uint64_t* rng_key,
+                                  int method, const uint8_t* use_jacobi, const double* RHS, int rhs_shared, double* X_out,
+                                  int32_t* status_out, int32_t* iters_out) {
+    int rc = check_ready(ctx, C, "maus_solve_shifted: bad C"); if (rc) return rc;
+    if (!sigma || !psi) return maus_fail(ctx, MAUS_E_ARG, "maus_solve_shifted: sigma / psi required");
+    const long long n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->sigma, sigma, (size_t)C * sizeof(cplx), cudaMemcpyHostToDevice, st));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->psi, psi, (size_t)C * 8, cudaMemcpyHostToDevice, st));
+    if (rng_key) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->keys, rng_key, (size_t)C * 8, cudaMemcpyHostToDevice, st));
+    else MAUS_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, (size_t)C * 8, st));
+    if (use_jacobi) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->jac, use_jacobi, (size_t)C, cudaMemcpyHostToDevice, st));
+    else MAUS_CUDA(ctx, cudaMemsetAsync(ctx->jac, 0, (size_t)C, st));
+    MAUS_CUDA(ctx, cudaMemsetAsync(ctx->status, 0, (size_t)C * 4, st));
+    MAUS_CUDA(ctx, cudaMemsetAsync(ctx->iters, 0, (size_t)C * 4, st));
+    const cplx* rhs; long long rstride;
+    if (RHS) {
+        // stage the host right-hand sides in Y (free at this point)
+        const long long cnt = rhs_shared ? 1 : C;
+        MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->Y, RHS, (size_t)cnt * n * sizeof(cplx), cudaMemcpyHostToDevice, st));
+        rhs = ctx->Y; rstride = rhs_shared ? 0 : n;
+    } else if (rhs_shared) {
+        if (!ctx->b_set) return maus_fail(ctx, MAUS_E_STATE, "maus_solve_shifted: rhs not set");
+        rhs = ctx->b; rstride = 0;
+    } else {
+        rhs = ctx->V; rstride = n;
+    }
+    const bool sparse = ctx->slot[0].sparse;
+    if ((rc = solve_device(ctx, C, method, rhs, rstride, nullptr, rng_key != nullptr))) return rc;
+    (void)sparse;
+    if (X_out) MAUS_CUDA(ctx, cudaMemcpyAsync(X_out, ctx->X, (size_t)C * n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    if (status_out) MAUS_CUDA(ctx, cudaMemcpyAsync(status_out, ctx->status, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+    if (iters_out) MAUS_CUDA(ctx, cudaMemcpyAsync(iters_out, ctx->iters, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(st));
+    return MAUS_OK;
+}
+
+extern "C" int maus_solve_with_R(maus_ctx* ctx, const double* sigma, const double* psi, const double* R_rowmajor,
+                                 const double* rhs, double* x_out, int32_t* status_out) {
+    int rc = check_ready(ctx, 1, "maus_solve_with_R"); if (rc) return rc;
+    if (!sigma || !psi || !R_rowmajor || !rhs) return maus_fail(ctx, MAUS_E_ARG, "maus_solve_with_R: bad argument");
+    if (!ctx->slot[0].dense) return maus_fail(ctx, MAUS_E_ARG, "maus_solve_with_R: dense matrix required");
+    const long long n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    const size_t bytes = (size_t)n * n * sizeof(cplx);
+    if (!ctx->Rcm) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&ctx->Rcm, bytes));
+    // stage R row-major in the LU workspace head, then transpose
+    int wb = 0;
+    if ((rc = ensure_lu_workspace(ctx, 1, &wb))) return rc;
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->W, R_rowmajor, bytes, cudaMemcpyHostToDevice, st));
+    MAUS_CUDA(ctx, vec_rowmajor_to_colmajor(ctx->W, ctx->Rcm, (int)n, st));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->sigma, sigma, sizeof(cplx), cudaMemcpyHostToDevice, st));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->psi, psi, 8, cudaMemcpyHostToDevice, st));
+    MAUS_CUDA(ctx, cudaMemsetAsync(ctx->status, 0, 4, st));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->Y, rhs, (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice, st));
+    if ((rc = maus_lu_solve(ctx, 1, ctx->sigma, ctx->psi, nullptr, ctx->Rcm, ctx->Y, n, ctx->X, ctx->status))) return rc;
+    if (x_out) MAUS_CUDA(ctx, cudaMemcpyAsync(x_out, ctx->X, (size_t)n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    if (status_out) MAUS_CUDA(ctx, cudaMemcpyAsync(status_out, ctx->status, 4, cudaMemcpyDeviceToHost, st));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(st));
+    return MAUS_OK;
+}
+
+static int residual_device(maus_ctx* ctx, long long C, int problem_type, int res_slot) {
+    int rc = maus_apply_matrix(ctx, res_slot, ctx->V, ctx->Y, C); if (rc) return rc;
+    if (problem_type == MAUS_SOLVE_LINEAR_SYSTEM && !ctx->b_set) return maus_fail(ctx, MAUS_E_STATE, "rhs not set");
+    MAUS_CUDA(ctx, vec_residual_finish(ctx->V, ctx->Y, (int)ctx->n, (int)C, problem_type, ctx->lambda, ctx->b, ctx->resid,
+                                       ctx->stream));
+    ctx->launches += 2;
+    return MAUS_OK;
+}
+
+extern "C" int maus_mix_residual(maus_ctx* ctx, int64_t C, int problem_type, const double* alpha, const double* lambda_old,
+                                 const uint8_t* skip, int res_slot, double* V_out, double* resid_out, double* mixnorm_out,
+                                 int32_t* status_out) {
+    int rc = check_ready(ctx, C, "maus_mix_residual: bad C"); if (rc) return rc;
+    if (!alpha) return maus_fail(ctx, MAUS_E_ARG, "maus_mix_residual: alpha required");
+    if (problem_type == MAUS_EIGENVALUE && !lambda_old) return maus_fail(ctx, MAUS_E_ARG, "maus_mix_residual: lambda required");
+    const long long n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->alpha, alpha, (size_t)C * 8, cudaMemcpyHostToDevice, st));
+    if (lambda_old) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->lambda, lambda_old, (size_t)C * sizeof(cplx), cudaMemcpyHostToDevice, st));
+    if (skip) {
+        std::vector<int> stat((size_t)C);
+        for (long long c = 0; c < C; ++c) stat[(size_t)c] = skip[c] ? MAUS_ST_SKIPPED : 0;
+        MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->status, stat.data(), (size_t)C * 4, cudaMemcpyHostToDevice, st));
+        MAUS_CUDA(ctx, cudaStreamSynchronize(st));
+    } else {
+        MAUS_CUDA(ctx, cudaMemsetAsync(ctx->status, 0, (size_t)C * 4, st));
+    }
+    MAUS_CUDA(ctx, vec_mix_normalise(ctx->V, ctx->X, (int)n, (int)C, problem_type, ctx->alpha, ctx->mixnorm, ctx->status, st));
+    ctx->launches += 1;
+    if ((rc = residual_device(ctx, C, problem_type, res_slot))) return rc;
+    if (V_out) MAUS_CUDA(ctx, cudaMemcpyAsync(V_out, ctx->V, (size_t)C * n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    if (resid_out) MAUS_CUDA(ctx, cudaMemcpyAsync(resid_out, ctx->resid, (size_t)C * 8, cudaMemcpyDeviceToHost, st));
+    if (mixnorm_out) MAUS_CUDA(ctx, cudaMemcpyAsync(mixnorm_out, ctx->mixnorm, (size_t)C * 8, cudaMemcpyDeviceToHost, st));
+    if (status_out) MAUS_CUDA(ctx, cudaMemcpyAsync(status_out, ctx->status, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(st));
+    return MAUS_OK;
+}
+
+extern "C" int maus_residual(maus_ctx* ctx, int64_t C, int problem_type, const double* V, const double* lambda, int res_slot,
+                             double* resid_out) {
+    int rc = check_ready(ctx, C, "maus_residual: bad C"); if (rc) return rc;
+    const long long n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    if (V) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->V, V, (size_t)C * n * sizeof(cplx), cudaMemcpyHostToDevice, st));
+    if (problem_type == MAUS_EIGENVALUE) {
+        if (!lambda) return maus_fail(ctx, MAUS_E_ARG, "maus_residual: lambda required");
+        MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->lambda, lambda, (size_t)C * sizeof(cplx), cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = residual_device(ctx, C, problem_type, res_slot))) return rc;
+    if (resid_out) MAUS_CUDA(ctx, cudaMemcpyAsync(resid_out, ctx->resid, (size_t)C * 8, cudaMemcpyDeviceToHost, st));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(st));
+    return MAUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fused generation step
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int maus_step(maus_ctx* ctx, int64_t C, int problem_type, int method, double* V_io, const double* alpha,
+                         const double* psi, const uint64_t* rng_key, const uint8_t* use_jacobi, int res_slot,
+                         double* lambda_out, double* resid_out, double* mixnorm_out, int32_t* status_out,
+                         int32_t* iters_out) {
+    int rc = check_ready(ctx, C, "maus_step: bad C"); if (rc) return rc;
+    if (!alpha || !psi) return maus_fail(ctx, MAUS_E_ARG, "maus_step: alpha / psi required");
+    if (problem_type != MAUS_EIGENVALUE && problem_type != MAUS_SOLVE_LINEAR_SYSTEM)
+        return maus_fail(ctx, MAUS_E_ARG, "maus_step: problem type");
+    const long long n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    if (V_io) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->V, V_io, (size_t)C * n * sizeof(cplx), cudaMemcpyHostToDevice, st));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->alpha, alpha, (size_t)C * 8, cudaMemcpyHostToDevice, st));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->psi, psi, (size_t)C * 8, cudaMemcpyHostToDevice, st));
+    if (rng_key) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->keys, rng_key, (size_t)C * 8, cudaMemcpyHostToDevice, st));
+    else MAUS_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, (size_t)C * 8, st));
+    if (use_jacobi) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->jac, use_jacobi, (size_t)C, cudaMemcpyHostToDevice, st));
+    else MAUS_CUDA(ctx, cudaMemsetAsync(ctx->jac, 0, (size_t)C, st));
+    MAUS_CUDA(ctx, cudaMemsetAsync(ctx->status, 0, (size_t)C * 4, st));
+    MAUS_CUDA(ctx, cudaMemsetAsync(ctx->iters, 0, (size_t)C * 4, st));
+
+    const cplx* rhs; long long rstride;
+    if (problem_type == MAUS_EIGENVALUE) {
+        // AMS:264-270: lambda = RQ(v); sigma = lambda
+        if ((rc = maus_apply_matrix(ctx, 0, ctx->V, ctx->Y, C))) return rc;
+        MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, ctx->status, st));
+        ctx->launches += 1;
+        MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->sigma, ctx->lambda, (size_t)C * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+        rhs = ctx->V; rstride = n;
+    } else {
+        if (!ctx->b_set) return maus_fail(ctx, MAUS_E_STATE, "maus_step: rhs not set");
+        MAUS_CUDA(ctx, cudaMemsetAsync(ctx->sigma, 0, (size_t)C * sizeof(cplx), st));
+        MAUS_CUDA(ctx, cudaMemsetAsync(ctx->lambda, 0, (size_t)C * sizeof(cplx), st));
+        rhs = ctx->b; rstride = 0;
+    }
+    if ((rc = solve_device(ctx, C, method, rhs, rstride, nullptr, rng_key != nullptr))) return rc;
+    MAUS_CUDA(ctx, vec_mix_normalise(ctx->V, ctx->X, (int)n, (int)C, problem_type, ctx->alpha, ctx->mixnorm, ctx->status, st));
+    ctx->launches += 1;
+    if ((rc = residual_device(ctx, C, problem_type, res_slot))) return rc;
+    if (V_io) MAUS_CUDA(ctx, cudaMemcpyAsync(V_io, ctx->V, (size_t)C * n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    if (lambda_out) MAUS_CUDA(ctx, cudaMemcpyAsync(lambda_out, ctx->lambda, (size_t)C * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    if (resid_out) MAUS_CUDA(ctx, cudaMemcpyAsync(resid_out, ctx->resid, (size_t)C * 8, cudaMemcpyDeviceToHost, st));
+    if (mixnorm_out) MAUS_CUDA(ctx, cudaMemcpyAsync(mixnorm_out, ctx->mixnorm, (size_t)C * 8, cudaMemcpyDeviceToHost, st));
+    if (status_out) MAUS_CUDA(ctx, cudaMemcpyAsync(status_out, ctx->status, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+    if (iters_out) MAUS_CUDA(ctx, cudaMemcpyAsync(iters_out, ctx->iters, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(st));
+    return MAUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// debug / parity hooks
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, const double* A, const double* B, double* Cm,
+                                int beta, int negate, int use_dmma) {
+    if (!ctx || !A || !B || !Cm || M <= 0 || N <= 0 || K <= 0 || batch <= 0) return maus_fail(ctx, MAUS_E_ARG, "maus_debug_zgemm");
+    cudaSetDevice(ctx->device);
+    cplx *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    const size_t ba = (size_t)M * K * batch * sizeof(cplx), bb = (size_t)K * N * batch * sizeof(cplx),
+                 bc = (size_t)M * N * batch * sizeof(cplx);
+    MAUS_CUDA(ctx, cudaMalloc(&dA, ba)); MAUS_CUDA(ctx, cudaMalloc(&dB, bb)); MAUS_CUDA(ctx, cudaMalloc(&dC, bc));
+    cudaStream_t st = ctx->stream;
+    MAUS_CUDA(ctx, cudaMemcpyAsync(dA, A, ba, cudaMemcpyHostToDevice, st));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(dB, B, bb, cudaMemcpyHostToDevice, st));
+    MAUS_CUDA(ctx, cudaMemcpyAsync(dC, Cm, bc, cudaMemcpyHostToDevice, st));
+    ZgemmParams p;
+    p.A = dA; p.lda = M; p.strideA = (long long)M * K;
+    p.B = dB; p.ldb = K; p.strideB = (long long)K * N;
+    p.C = dC; p.ldc = M; p.strideC = (long long)M * N;
+    p.M = M; p.N = N; p.K = K; p.batch = batch; p.beta = beta; p.negate = negate;
+    cudaError_t e = use_dmma ? zgemm_dmma_launch(p, st) : zgemm_simple_launch(p, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Cm, dC, bc, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    ctx->launches += 1;
+    if (e != cudaSuccess) return maus_fail(ctx, MAUS_E_CUDA, "maus_debug_zgemm", e);
+    return MAUS_OK;
+}

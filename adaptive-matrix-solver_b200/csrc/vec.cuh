@@ -1,0 +1,25 @@
+// vec.cuh -- fused reduction / elementwise kernels of the candidate step (Rayleigh quotient, mix + normalise,
+// residual norms; AMS:264-268, 280-285, 295-299) and layout helpers.
+#pragma once
+#include "common.cuh"
+
+// out (n x n column-major) = transpose-free re-layout of in (n x n row-major)
+cudaError_t vec_rowmajor_to_colmajor(const cplx* in_rm, cplx* out_cm, int n, cudaStream_t stream);
+
+// lambda_c = <v_c, y_c> / <v_c, v_c>  (0 when |<v,v>| < 1e-12), vnorm2_c = <v_c, v_c>; status V_COLLAPSED when
+// sqrt(<v,v>) < 1e-10.  V, Y: [C][n].
+cudaError_t vec_rq_finish(const cplx* V, const cplx* Y, int n, int C, cplx* lambda, double* vnorm2, int* status,
+                          cudaStream_t stream);
+
+// eigen : v <- (1-a) v + a x ; nv = ||v||_2 ; v /= nv when nv > 1e-10 else status MIX_COLLAPSED (v left unnormalised)
+// linear: v <- (1-a) v + a x ; nv = ||v||_2 (reported only)
+// candidates with status[c] != 0 on entry are left untouched.
+cudaError_t vec_mix_normalise(cplx* V, const cplx* X, int n, int C, int problem_type, const double* alpha,
+                              double* mixnorm, int* status, cudaStream_t stream);
+
+// eigen : r_c = || y_c - lambda_c v_c ||_2       linear: r_c = || y_c - b ||_2
+cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda,
+                                const cplx* b, double* resid, cudaStream_t stream);
+
+// Y[c] = A_rowmajor * V[c]: HBM-bound batched matvec, one warp per matrix row, CB candidates per pass
+cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, cplx* Y, int n, int C, cudaStream_t stream);

@@ -1,0 +1,17 @@
+// zgemm.cuh -- batched complex128 GEMM on the FP64 tensor pipe (DMMA) with TMA-bulk staged panels.
+#pragma once
+#include "common.cuh"
+
+struct ZgemmParams {
+    const cplx* A; long long lda, strideA;   // M x K, column-major
+    const cplx* B; long long ldb, strideB;   // K x N, column-major
+    cplx* C;       long long ldc, strideC;   // M x N, column-major
+    int M, N, K, batch;
+    int beta;      // 0: C = s*A*B        1: C = C + s*A*B
+    int negate;    // s = -1 when set, else +1
+};
+
+// Tensor-pipe kernel (any M, N, K >= 1).  In-place use (C aliasing B) is safe when M <= 128 (one row tile).
+cudaError_t zgemm_dmma_launch(const ZgemmParams& p, cudaStream_t stream);
+// Plain FP64-FMA kernel, independent code path used by the tests to cross-check the tensor-pipe kernel.
+cudaError_t zgemm_simple_launch(const ZgemmParams& p, cudaStream_t stream);

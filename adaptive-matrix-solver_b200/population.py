@@ -1,0 +1,290 @@
+"""Seam B: one batched GPU generation behind the reference's candidate objects.
+
+``step_population(candidates, M, b, strat_params, problem_knowledge, engine)`` is the drop-in for the loop at
+AMS:574-576::
+
+    for candidate in self.candidates:
+        if candidate.state not in [CONVERGED, RETIRED]:
+            candidate.update_solution_step(self.M, self.b, self.strat_params, self.problem_knowledge)
+
+It performs, for every live EIGENVALUE (non-Hermitian) / SOLVE_LINEAR_SYSTEM candidate, exactly what
+``SolutionCandidate.update_solution_step`` does (AMS:145-153, 224-225, 256-299, 303-331) and writes back every field
+the reference mutates, so ``_update_global_diagnostics`` / ``_adjust_global_strategy`` / ``_manage_candidates`` run
+unmodified afterwards.  All numerics (Rayleigh quotient, shifted solve, mix, normalise, residual) run in ONE fused
+CUDA call for the whole population; only the rare failures walk the Psi ladder (AMS:43-104) through the granular
+calls.  Hermitian-eigen and SVD candidates are passed to the reference method untouched.
+
+Deliberate deviations (DESIGN.md section "Deviations"): the dense Psi perturbation (AMS:49) comes from a
+counter-based device RNG, not from the global numpy stream; host RNG draws therefore happen only for the
+re-initialisations (AMS:260, 283, 293), in candidate order.
+"""
+import numpy as np
+
+from . import _abi
+from .constants import (PSI_EPSILON_BASE, MAX_PSI_ATTEMPTS, MAX_STUCK_FOR_RETIREMENT, CONVERGENCE_RESIDUAL_TOL,
+                        LU_MAX_N, psi_magnitude)
+from .solver import GpuInverseIterateSolver
+
+_METHOD = {'direct_solve': _abi.METHOD_LU, 'iterative_gmres': _abi.METHOD_GMRES}
+
+
+def _is_sparse(A):
+    try:
+        import scipy.sparse as sp
+        return sp.issparse(A)
+    except Exception:  # pragma: no cover
+        return False
+
+
+class _MatrixCache:
+    """Uploads a matrix only when the object behind the reference's ``self.M`` changes (AMS:646 swaps it)."""
+
+    def __init__(self):
+        self.obj = [None, None]
+        self.form = [None, None]
+
+    def ensure(self, engine, A, slot, form):
+        if self.obj[slot] is A and self.form[slot] == form:
+            return
+        if form == 'dense' and _is_sparse(A):
+            engine.set_matrix(A.toarray(), slot)
+        else:
+            engine.set_matrix(A, slot)
+        self.obj[slot] = A
+        self.form[slot] = form
+        if slot == 0:
+            self.obj[1] = None      # n may have changed; slot 1 is re-uploaded on demand
+
+
+def _key(cand_id, generation, attempt):
+    return ((int(cand_id) & 0xffffffff) << 32) | ((int(generation) & 0xffffff) << 8) | (int(attempt) & 0xff)
+
+
+def _ladder(engine, ptype, v_or_x, lam, stuck, base_psi, max_attempts, pref, matrix_sparse_semantics, cand_id,
+            first_method_failed=True):
+    """AMS:43-104 for ONE candidate whose attempt-0 try with the preferred method already failed on the device.
+    Returns (x or None, num_psi_attempts)."""
+    fallback = 'iterative_gmres' if pref == 'direct_solve' else 'direct_solve'
+    method, attempts = pref, 0
+    pending_failure = first_method_failed
+    engine.upload_vectors(v_or_x[None, :])
+    while attempts < max_attempts:
+        if not pending_failure:
+            psi = psi_magnitude(base_psi, attempts, stuck)
+            key = None if matrix_sparse_semantics else [_key(cand_id, engine.generation, attempts + 1)]
+            m = _METHOD.get(method)
+            if m is None or (m == _abi.METHOD_LU and engine.is_sparse):
+                status = _abi.ST_ZERO_PIVOT
+                X = None
+            else:
+                X, st, _ = engine.solve_shifted([lam if ptype == _abi.EIGENVALUE else 0j], [complex(psi).real],
+                                                rng_key=key, method=m, use_jacobi=[1 if stuck > 1 else 0],
+                                                RHS=None, rhs_shared=(ptype == _abi.SOLVE_LINEAR_SYSTEM))
+                status = int(st[0])
+            if status == _abi.ST_OK:
+                return X[0], attempts
+        pending_failure = False
+        if method == pref and pref != fallback and attempts == 0:          # AMS:99-102
+            method = fallback
+            attempts = 0
+            continue
+        attempts += 1                                                      # AMS:103
+    return None, attempts
+
+
+def step_population(candidates, M, b, strat_params, problem_knowledge, engine, cache=None):
+    """Batched equivalent of the loop AMS:574-576.  Returns the number of candidates stepped on the GPU."""
+    if not candidates:
+        return 0
+    State = type(candidates[0]).State
+    live = [c for c in candidates if c.state not in (State.CONVERGED, State.RETIRED)]          # AMS:575
+    hermitian = bool(problem_knowledge.get('is_hermitian', False))
+    gpu = []
+    for c in live:
+        pt = c.problem_type.value
+        if pt == _abi.SOLVE_LINEAR_SYSTEM or (pt == _abi.EIGENVALUE and not hermitian):
+            gpu.append(c)
+        else:
+            # Hermitian shortcut (AMS:155-221) and SVD sweep (AMS:227-255) are not on the hot path: untouched
+            c.update_solution_step(M, b, strat_params, problem_knowledge)
+    if not gpu:
+        return 0
+    cache = cache if cache is not None else getattr(engine, "_matrix_cache", None)
+    if cache is None:
+        cache = engine._matrix_cache = _MatrixCache()
+
+    ptype = gpu[0].problem_type.value
+    N = gpu[0].N_diag
+    aggr = strat_params.get('overall_psi_aggression_factor', 1.0)                              # AMS:149-152
+    max_retries = strat_params.get('max_psi_retries', MAX_PSI_ATTEMPTS)
+    pref = problem_knowledge.get('local_solver_preference', 'direct_solve')
+    is_sparse = bool(problem_knowledge.get('is_sparse_problem', False))
+    base_psi = PSI_EPSILON_BASE * aggr                                                         # AMS:224
+    conv_tol = strat_params.get('current_convergence_threshold', CONVERGENCE_RESIDUAL_TOL)
+
+    # matrix residency.  Direct solves need the dense form; a sparse problem that prefers the direct solver
+    # (reference: SuperLU, AMS:57) is densified when it fits the batched LU, otherwise that try fails -> GMRES.
+    m_sparse = _is_sparse(M)
+    if pref == 'direct_solve' and m_sparse and N <= LU_MAX_N:
+        form = 'dense'
+    else:
+        form = 'sparse' if m_sparse else 'dense'
+    cache.ensure(engine, M, 0, form)
+    if ptype == _abi.SOLVE_LINEAR_SYSTEM:
+        engine.set_rhs(b)
+
+    for c in gpu:
+        c.b_vector = b                                                                         # AMS:146
+        c.prev_residual = c.residual_k                                                         # AMS:147
+
+    # candidates are grouped by the matrix their residual uses (ctor-time matrix, AMS:118, 295)
+    groups = {}
+    for c in gpu:
+        key = 0 if c.problem_matrix is M else id(c.problem_matrix)
+        groups.setdefault(key, []).append(c)
+
+    for gkey, cands in groups.items():
+        res_slot = _abi.SLOT_CURRENT
+        if gkey != 0:
+            cache.ensure(engine, cands[0].problem_matrix, 1, 'sparse' if _is_sparse(cands[0].problem_matrix) else 'dense')
+            res_slot = _abi.SLOT_CTOR
+        _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, res_slot)
+    return len(gpu)
+
+
+def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, res_slot):
+    C_ = len(cands)
+    eigen = ptype == _abi.EIGENVALUE
+    V = np.empty((C_, N), dtype=np.complex128)
+    for i, c in enumerate(cands):
+        if eigen:
+            if np.linalg.norm(c.v_k) < 1e-10:                                                  # AMS:259-263
+                c.v_k = (np.random.rand(N) + 1j * np.random.rand(N))
+                c.v_k /= np.linalg.norm(c.v_k)
+                c.stuck_counter += 1
+                c.num_resets += 1
+                print(f"Candidate {c.id}: Eigenvector collapsed, reinitialized randomly before InverseIterateSolver.")
+            V[i] = c.v_k
+        else:
+            V[i] = c.x_k
+    V_before = V.copy()
+    stuck = np.array([c.stuck_counter for c in cands], dtype=np.int64)
+    alpha = np.array([complex(c.alpha_local_step).real for c in cands], dtype=np.float64)
+    psi0 = np.array([complex(psi_magnitude(base_psi, 0, int(s))).real for s in stuck], dtype=np.float64)
+    gen = engine.generation
+    keys = None if is_sparse else np.array([_key(c.id, gen, 0) for c in cands], dtype=np.uint64)
+    method0 = _METHOD.get(pref)
+    if method0 is None or (method0 == _abi.METHOD_LU and engine.is_sparse):
+        # unknown method / sparse-direct beyond the LU limit: the first try fails for everybody (AMS:92, 98)
+        out = dict(lam=engine.rq(V)[0] if eigen else np.zeros(C_, dtype=np.complex128),
+                   resid=np.full(C_, np.inf), mixnorm=np.zeros(C_), status=np.full(C_, _abi.ST_ZERO_PIVOT, dtype=np.int32),
+                   iters=np.zeros(C_, dtype=np.int32))
+    else:
+        out = engine.step(ptype, alpha, psi0, V=V, rng_key=keys, method=method0,
+                          use_jacobi=(stuck > 1).astype(np.uint8), res_slot=res_slot)
+    lam, resid, status = out["lam"], out["resid"], out["status"]
+
+    for i, c in enumerate(cands):
+        st = int(status[i])
+        solved, retries, new_vec = (st == _abi.ST_OK), 0, None
+        if eigen:
+            c.lambda_k = np.complex128(lam[i])                                                  # AMS:268 (0 when |<v,v>| tiny)
+        need_residual = False
+        if st in (_abi.ST_ZERO_PIVOT, _abi.ST_NONFINITE, _abi.ST_GMRES_NOCONV):
+            # the preferred method failed at attempt 0: walk the rest of the ladder for this candidate
+            x, retries = _ladder(engine, ptype, V_before[i], complex(lam[i]), int(stuck[i]), base_psi, max_retries,
+                                 pref, is_sparse, c.id)
+            if x is not None:
+                Vn, r1, mixn, st1 = engine.mix_residual(ptype, [alpha[i]], [lam[i]], res_slot=res_slot)
+                V[i] = Vn[0]
+                resid[i] = r1[0]
+                st = int(st1[0])
+                solved = True
+        if solved:
+            c.local_psi_retries_needed = retries                                                # AMS:278
+            if eigen:
+                if st == _abi.ST_MIX_COLLAPSED:                                                 # AMS:283
+                    c.v_k = (np.random.rand(N) + 1j * np.random.rand(N)) / np.sqrt(N)
+                    need_residual = True
+                else:
+                    c.v_k = V[i].copy()                                                         # AMS:280-282
+            else:
+                c.x_k = V[i].copy()                                                             # AMS:285
+            c.stuck_counter = max(0, c.stuck_counter - 1)                                       # AMS:286
+        else:
+            # RuntimeError branch, AMS:287-293 (V_COLLAPSED cannot happen: the guard above ran on the host)
+            c.stuck_counter += 1
+            c.w_k *= 0.001
+            c.alpha_local_step = max(c.alpha_local_step * 0.5, 1e-6)
+            if c.stuck_counter >= MAX_STUCK_FOR_RETIREMENT:
+                c.state = State.RETIRED
+                c.num_resets += 1
+            else:
+                c.state = State.STUCK
+                c.initialize_random_solution()
+            need_residual = True
+        if need_residual:                                                                       # AMS:295-299
+            vec = c.v_k if eigen else c.x_k
+            resid[i] = engine.residual(ptype, vec[None, :], [c.lambda_k] if eigen else None, res_slot=res_slot)[0]
+        c.residual_k = np.float64(resid[i])
+        c.param_history.append(c.get_current_solution_params())                                # AMS:303-304
+        c.residual_history.append(c.residual_k)
+        _adapt_and_test(c, State, conv_tol)
+
+
+def _adapt_and_test(c, State, conv_tol):
+    """AMS:306-331, scalar host logic kept bit-identical to the reference."""
+    if c.prev_residual > 1e-10:
+        if c.residual_k < c.prev_residual * 0.9:
+            c.alpha_local_step = min(c.alpha_local_step * 1.1, 1.0)
+            if c.state != State.CONVERGED:
+                c.state = State.REFINING
+        elif c.residual_k > c.prev_residual * 1.5 and c.prev_residual > 1e-5:
+            c.alpha_local_step = max(c.alpha_local_step * 0.5, 1e-6)
+            if c.state != State.CONVERGED:
+                c.state = State.STUCK
+        else:
+            c.alpha_local_step = max(c.alpha_local_step * 0.95, 1e-6)
+            if c.state not in [State.CONVERGED, State.STUCK, State.RETIRED]:
+                c.state = State.EXPLORING
+    params = c.get_current_solution_params()
+    finite = False
+    if params is not None:
+        finite = True
+        for p in params:
+            if p is None:
+                finite = False
+                break
+            if isinstance(p, np.ndarray):
+                if not np.all(np.isfinite(p)):
+                    finite = False
+                    break
+            elif not np.isfinite(p):
+                finite = False
+                break
+    if c.residual_k < conv_tol and finite:
+        c.state = State.CONVERGED
+        c.w_k = 1.0
+        c.stuck_counter = 0
+        c.alpha_local_step = 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# drop-in installation
+# ---------------------------------------------------------------------------------------------------------------
+def install_dropin(ams_module, engine):
+    """Seam A: rebind the module-global solver name the reference looks up on every step (AMS:224)."""
+    GpuInverseIterateSolver.bind_engine(engine)
+    ams_module.InverseIterateSolver = GpuInverseIterateSolver
+    return ams_module
+
+
+def gpu_generation(maus_solver, iteration, engine):
+    """One generation of ``MAUS_Solver.evolve`` (the body of the loop at AMS:572-577) with the candidate loop
+    executed by ``step_population``.  ``evolve`` itself cannot be used: it reads an undefined global (AMS:583)."""
+    maus_solver._update_global_diagnostics(iteration)
+    maus_solver._adjust_global_strategy(iteration)
+    n = step_population(maus_solver.candidates, maus_solver.M, maus_solver.b, maus_solver.strat_params,
+                        maus_solver.problem_knowledge, engine)
+    maus_solver._manage_candidates(iteration)
+    return n

@@ -1,0 +1,161 @@
+/*
+ * maus_b200.h -- C ABI of libmaus_b200.so: the B200 (sm_100a) implementation of ONE hot path of
+ * Kier73/Adaptive-Matrix-Solver ("MAUS"): the per-candidate Psi-regularised shifted inverse-iteration step.
+ *
+ * The reference (AMS = Adaptive_Matrix_Solver_0.1.py) is pure Python and has no FFI; the seams this library
+ * sits behind are Python names:
+ *   Seam A  InverseIterateSolver.solve                 AMS:39-104   -> maus_solve_shifted (C = 1)
+ *   Seam B  the per-candidate loop of MAUS_Solver.evolve AMS:574-576 -> maus_step (all live candidates at once)
+ * Each entry point below cites the reference lines it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain C, no exceptions; every function returns 0 on success, a negative MAUS_E_* code on failure;
+ *     maus_last_error() returns the text of the last failure of that context.
+ *   - complex128 = two consecutive doubles (re, im), exactly numpy's layout.  All host buffers are caller-owned,
+ *     C-contiguous; "V[C][n]" means candidate c's vector is the n complex numbers starting at V + 2*n*c.
+ *   - one context = one GPU = one host thread (one process per GPU; multi-GPU is candidate sharding done by
+ *     the host layer with torch.distributed / NCCL, see adaptive-matrix-solver_b200/dist.py).
+ *   - there is NO CPU fallback: without a CUDA device maus_create fails with MAUS_E_CUDA.
+ */
+#ifndef MAUS_B200_H
+#define MAUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct maus_ctx maus_ctx;
+
+/* error codes */
+#define MAUS_OK            0
+#define MAUS_E_ARG        -1   /* bad argument (NULL pointer, size, unsupported combination) */
+#define MAUS_E_CUDA       -2   /* CUDA runtime error, text in maus_last_error */
+#define MAUS_E_STATE      -3   /* call order (e.g. step before set_dense) */
+#define MAUS_E_NOMEM      -4   /* device workspace does not fit */
+
+/* per-candidate status words written by the solve / step entry points (0 = success).  They let the host keep
+ * the reference's retry ladder (AMS:43, 98-104) with identical semantics:
+ *   ZERO_PIVOT   <-> scipy.linalg.solve raising LinAlgError (exactly singular), AMS:59/98
+ *   NONFINITE    <-> "Solution vector not finite" ValueError, AMS:94-95
+ *   GMRES_NOCONV <-> gmres info != 0 -> LinAlgError, AMS:90
+ *   V_COLLAPSED  <-> ||v|| < 1e-10 before the step, AMS:259 (host re-initialises from its RNG and re-submits)
+ *   MIX_COLLAPSED<-> ||(1-a)v + a x|| <= 1e-10 after the mix, AMS:283 (host replaces v from its RNG)
+ *   SKIPPED      <-> candidate was masked out of this call */
+#define MAUS_ST_OK             0
+#define MAUS_ST_ZERO_PIVOT     1
+#define MAUS_ST_NONFINITE      2
+#define MAUS_ST_GMRES_NOCONV   3
+#define MAUS_ST_V_COLLAPSED    4
+#define MAUS_ST_MIX_COLLAPSED  5
+#define MAUS_ST_SKIPPED        6
+
+/* problem types, AMS:10-13 */
+#define MAUS_EIGENVALUE          1
+#define MAUS_SOLVE_LINEAR_SYSTEM 2
+
+/* solver methods, AMS:35-36 ('direct_solve' / 'iterative_gmres') */
+#define MAUS_METHOD_LU     0
+#define MAUS_METHOD_GMRES  1
+
+/* matrix slots: 0 = current_matrix_A of the step (AMS:145), 1 = the candidate's ctor-time problem_matrix used by
+ * the residual (AMS:118, 295).  Slot 1 defaults to slot 0 until set. */
+#define MAUS_SLOT_CURRENT  0
+#define MAUS_SLOT_CTOR     1
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+int         maus_create(maus_ctx** out, int device);
+int         maus_destroy(maus_ctx* ctx);
+const char* maus_last_error(maus_ctx* ctx);
+/* cap on device workspace for the batched LU (bytes); 0 = default (60% of free memory). */
+int         maus_set_workspace_limit(maus_ctx* ctx, int64_t bytes);
+/* device id, SM count, bytes of device memory currently held by the context */
+int         maus_info(maus_ctx* ctx, int* device, int* sm_count, int64_t* bytes_held);
+
+/* page-locked host buffers for the host<->device copies of maus_step / maus_upload_vectors (optional; any host
+ * pointer works, pinned memory makes the copies asynchronous and full-speed) */
+void*       maus_alloc_pinned(int64_t bytes);
+void        maus_free_pinned(void* p);
+
+/* ---- problem upload (replaces the numpy / scipy.sparse objects self.M, self.b of AMS:342-346) --------------- */
+/* dense n x n complex128, row-major (numpy C order).  Kept on the device both row-major (matvec) and
+ * column-major (LU). */
+int maus_set_dense(maus_ctx* ctx, int slot, int64_t n, const double* A_rowmajor);
+/* sparse CSC as scipy.sparse.csc_matrix holds it (AMS:358); converted once to CSR on the device. */
+int maus_set_csc(maus_ctx* ctx, int slot, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowidx,
+                 const double* vals);
+/* right-hand side b of SOLVE_LINEAR_SYSTEM (AMS:346) */
+int maus_set_rhs(maus_ctx* ctx, const double* b);
+
+/* ---- resident candidate vectors --------------------------------------------------------------------------- */
+/* copy C candidate vectors (v_k for eigen, x_k for linear; AMS:120) to / from the device-resident population. */
+int maus_upload_vectors(maus_ctx* ctx, int64_t C, const double* V);
+int maus_download_vectors(maus_ctx* ctx, int64_t C, double* V);
+
+/* ---- granular pieces (the host keeps the control flow of AMS:39-104 / 145-331) ---------------------------- */
+/* Rayleigh quotient lambda_c = <v,Av>/<v,v> (lambda = 0 when |<v,v>| < 1e-12) and <v,v>, AMS:264-268.
+ * V == NULL uses the resident vectors. */
+int maus_rq(maus_ctx* ctx, int64_t C, const double* V, double* lambda_out, double* vnorm2_out);
+
+/* x_c = (A - sigma_c I + psi_c I + R_c)^-1 rhs_c for C candidates, AMS:44-59, 61-97 (one attempt of the ladder):
+ *   sigma  [C] complex : lambda_k for eigen (AMS:270), 0 for linear (AMS:274)
+ *   psi    [C] real    : AMS:44 (its imaginary part is identically 0)
+ *   rng_key[C] uint64  : counter-based (Philox4x32-10) key of the dense perturbation R_c of AMS:49; the host
+ *                        passes (candidate id, generation, attempt) packed into 64 bits.  Sparse: R = 0 (AMS:47).
+ *   method             : MAUS_METHOD_LU (AMS:59) or MAUS_METHOD_GMRES (AMS:61-90, rtol 1e-8, restart 20, maxiter 50)
+ *   use_jacobi [C]     : request the Jacobi preconditioner of AMS:64-86 (host passes stuck_counter > 1); the
+ *                        finite / |d| > 1e-12 tests are done on the device.  May be NULL.
+ *   RHS                : [C][n], or [n] shared when rhs_shared != 0 (AMS:271 / 275); NULL = resident vectors
+ *                        (eigen) or the uploaded b (linear, with rhs_shared != 0)
+ *   X_out  [C][n]      : may be NULL (result stays on the device for maus_mix_residual)
+ *   status_out [C], iters_out [C] (gmres inner iterations; 0 for LU) */
+int maus_solve_shifted(maus_ctx* ctx, int64_t C, const double* sigma, const double* psi, const uint64_t* rng_key,
+                       int method, const uint8_t* use_jacobi, const double* RHS, int rhs_shared,
+                       double* X_out, int32_t* status_out, int32_t* iters_out);
+
+/* debug / parity: same as the LU branch above for ONE candidate but with the perturbation R supplied by the
+ * host (n x n complex128 row-major, e.g. drawn from np.random exactly as AMS:49 does). */
+int maus_solve_with_R(maus_ctx* ctx, const double* sigma, const double* psi, const double* R_rowmajor,
+                      const double* rhs, double* x_out, int32_t* status_out);
+
+/* damped mix + normalise (AMS:280-285) and residual (AMS:295-299) on the resident vectors and the resident
+ * result of the last maus_solve_shifted:
+ *   eigen : v <- (1-a) v + a x ; nv = ||v|| ; v <- v/nv if nv > 1e-10 ; r = || A_res v - lambda_old v ||
+ *   linear: x <- (1-a) x + a x_new ; r = || A_res x - b ||
+ * skip[c] != 0 leaves candidate c untouched (failed solve; status SKIPPED).  res_slot selects A_res. */
+int maus_mix_residual(maus_ctx* ctx, int64_t C, int problem_type, const double* alpha, const double* lambda_old,
+                      const uint8_t* skip, int res_slot, double* V_out, double* resid_out, double* mixnorm_out,
+                      int32_t* status_out);
+
+/* residual only (AMS:295-299) for the resident vectors -- used after the host replaced collapsed vectors. */
+int maus_residual(maus_ctx* ctx, int64_t C, int problem_type, const double* V, const double* lambda,
+                  int res_slot, double* resid_out);
+
+/* ---- fused fast path: one generation of AMS:574-576 for C candidates, all attempts = 0 -------------------- */
+/* rq -> solve -> mix -> normalise -> residual.  V_io == NULL keeps everything resident (no H2D / D2H of vectors).
+ * Candidates whose status != 0 are left unchanged (the host runs the ladder for them with the granular calls). */
+int maus_step(maus_ctx* ctx, int64_t C, int problem_type, int method, double* V_io, const double* alpha,
+              const double* psi, const uint64_t* rng_key, const uint8_t* use_jacobi, int res_slot,
+              double* lambda_out, double* resid_out, double* mixnorm_out, int32_t* status_out, int32_t* iters_out);
+
+/* debug / parity: C = beta*C + s*A*B on column-major complex128 host matrices (A: M x K, B: K x N, C: M x N,
+ * `batch` of each, densely packed) through the tensor-pipe kernel (use_dmma != 0) or the plain FP64-FMA kernel. */
+int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, const double* A, const double* B, double* C,
+                     int beta, int negate, int use_dmma);
+
+/* ---- instrumentation --------------------------------------------------------------------------------------- */
+/* number of kernels this context launched since creation (bench.py's gpu_launches) */
+int64_t maus_launch_count(maus_ctx* ctx);
+/* device-time (ms, CUDA events on the context's stream) and launch count of the LU trailing-update kernel and
+ * the batched matvec kernel accumulated since the last reset -- the roofline numbers of bench.py */
+int maus_profile_reset(maus_ctx* ctx, int enable);
+int maus_profile_read(maus_ctx* ctx, double* lu_gemm_ms, int64_t* lu_gemm_launches, double* lu_gemm_flops,
+                      double* matvec_ms, int64_t* matvec_launches, double* matvec_bytes);
+/* the context's CUDA stream as a void* (cudaStream_t) so a host layer can order its own work after it */
+void* maus_stream(maus_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAUS_B200_H */
