@@ -41,11 +41,14 @@ __global__ void __launch_bounds__(256) lu_build_aug_kernel(cplx* W, long long st
     }
     const cplx a = Acm[off];
     for (int b = 0; b < batch; ++b) {
+        // same association as the reference: T = A - lambda*I (AMS:270); reg = psi*I + perturb (AMS:50); H = T + reg (AMS:52)
         cplx h = a;
         const double ps = psi[b];
-        if (i == j) { h.x += ps - sigma[b].x; h.y -= sigma[b].y; }
-        if (R_cm) { h.x += R_cm[off].x; h.y += R_cm[off].y; }
-        else if (keys) { cplx r = psi_perturbation(keys[b], (uint32_t)i, (uint32_t)j, ps); h.x += r.x; h.y += r.y; }
+        if (i == j) { h.x -= sigma[b].x; h.y -= sigma[b].y; }
+        cplx reg = cmake((i == j) ? ps : 0.0, 0.0);
+        if (R_cm) { reg.x += R_cm[off].x; reg.y += R_cm[off].y; }
+        else if (keys) { cplx r = psi_perturbation(keys[b], (uint32_t)i, (uint32_t)j, ps); reg.x += r.x; reg.y += r.y; }
+        h.x += reg.x; h.y += reg.y;
         W[b * strideW + off] = h;
     }
 }
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(LU_NB) lu_trtri_kernel(const cplx* __restrict_
     const int b = blockIdx.x, c = threadIdx.x;
     const cplx* L = W + (long long)b * strideW + (long long)k0 * n + k0;   // L[r + p*n]
     if (c < jb) X[(c * (c + 1)) / 2 + c] = cmake(1.0, 0.0);
-    if (jb > 1 && c < 1) rowbuf[c] = L[1 + (long long)c * n];
+    if (jb > 1 && c < 1) rowbuf[LU_NB + c] = L[1 + (long long)c * n];     // row 1 lives in buffer (1 & 1)
     __syncthreads();
     for (int r = 1; r < jb; ++r) {
         const cplx* lr = rowbuf + (r & 1) * LU_NB;

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_dmma_kernel(ZgemmParams p) 
 #pragma unroll
                 for (int qa = 0; qa < 8; ++qa) af[qa] = a_s[2 * (kc * LDSA + arow + 8 * qa) + (t & 1)];
 #pragma unroll
-                for (int qb = 0; qb < 4; ++qb) bf[qb] = b_s[2 * ((bcol + 2 * qb) * LDSB + kc) + comp] * sgn;
+                for (int qb = 0; qb < 4; ++qb) bf[qb] = b_s[2 * ((bcol + 4 * qb) * LDSB + kc) + comp] * sgn;
 #pragma unroll
                 for (int qa = 0; qa < 8; ++qa)
 #pragma unroll
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) zgemm_dmma_kernel(ZgemmParams p) 
 #pragma unroll
                 for (int qa = 0; qa < 8; ++qa) af[qa] = ok ? a_s[2 * (kc * LDSA + arow + 8 * qa) + (t & 1)] : 0.0;
 #pragma unroll
-                for (int qb = 0; qb < 4; ++qb) bf[qb] = ok ? b_s[2 * ((bcol + 2 * qb) * LDSB + kc) + comp] * sgn : 0.0;
+                for (int qb = 0; qb < 4; ++qb) bf[qb] = ok ? b_s[2 * ((bcol + 4 * qb) * LDSB + kc) + comp] * sgn : 0.0;
 #pragma unroll
                 for (int qa = 0; qa < 8; ++qa)
 #pragma unroll
