@@ -16,7 +16,7 @@ SLOT_CURRENT, SLOT_CTOR = 0, 1
 EXPORTS = [
     "maus_create", "maus_destroy", "maus_last_error", "maus_set_workspace_limit", "maus_info", "maus_alloc_pinned",
     "maus_free_pinned", "maus_set_dense", "maus_set_csc", "maus_set_rhs", "maus_upload_vectors",
-    "maus_download_vectors", "maus_rq", "maus_solve_shifted", "maus_solve_with_R", "maus_mix_residual",
+    "maus_download_vectors", "maus_download_vector_range", "maus_rq", "maus_solve_shifted", "maus_solve_with_R", "maus_mix_residual",
     "maus_residual", "maus_step", "maus_launch_count", "maus_profile_reset", "maus_profile_read", "maus_stream", "maus_debug_zgemm",
 ]
 
@@ -67,6 +67,7 @@ def load_library():
         "maus_set_rhs": (i32, [vp, dp]),
         "maus_upload_vectors": (i32, [vp, i64, dp]),
         "maus_download_vectors": (i32, [vp, i64, dp]),
+        "maus_download_vector_range": (i32, [vp, i64, i64, dp]),
         "maus_rq": (i32, [vp, i64, dp, dp, dp]),
         "maus_solve_shifted": (i32, [vp, i64, dp, dp, u64p, i32, u8p, dp, i32, dp, i32p, i32p]),
         "maus_solve_with_R": (i32, [vp, dp, dp, dp, dp, dp, i32p]),

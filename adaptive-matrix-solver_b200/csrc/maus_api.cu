@@ -344,6 +344,16 @@ extern "C" int maus_download_vectors(maus_ctx* ctx, int64_t C, double* V) {
     return MAUS_OK;
 }
 
+extern "C" int maus_download_vector_range(maus_ctx* ctx, int64_t first, int64_t count, double* V) {
+    if (!ctx || !V || first < 0 || count <= 0 || first + count > ctx->Ccap)
+        return maus_fail(ctx, MAUS_E_ARG, "maus_download_vector_range: bad argument");
+    cudaSetDevice(ctx->device);
+    MAUS_CUDA(ctx, cudaMemcpyAsync(V, ctx->V + first * ctx->n, (size_t)count * ctx->n * sizeof(cplx), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MAUS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // matrix application
 // ------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,150 @@
+"""Candidate-population sharding across the GPUs of one box.
+
+Candidates never read each other inside a step (AMS:574-576 touches only ``self`` + shared read-only inputs), so the
+population shards with NO data-path collective: live candidate i -> rank ``i mod G``, the matrix is replicated, every
+rank runs the fused CUDA step on its own shard.  The only exchange is one all-gather per generation of the updated
+candidate records (+ vectors), which feeds the host-side diagnostics / pruning of the reference
+(``_update_global_diagnostics`` AMS:424-475, ``_manage_candidates`` AMS:504-549) that every rank replays identically.
+
+One process per GPU, ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+from . import _abi
+from .population import step_population
+
+# float64 record per candidate exchanged each generation
+REC_FIELDS = ("lambda_re", "lambda_im", "residual", "prev_residual", "alpha_re", "alpha_is_complex", "stuck", "retries",
+              "resets", "w", "state", "hist_added")
+NREC = len(REC_FIELDS)
+
+
+class Shard:
+    def __init__(self, rank=0, world=1, device=None):
+        self.rank, self.world, self.device = int(rank), int(world), device
+
+    def owned(self, live_count):
+        """indices (into the live list) this rank steps: round-robin, re-balanced every generation"""
+        return list(range(self.rank, live_count, self.world))
+
+    # ---- collectives ----------------------------------------------------------------------------------------
+    def _dist(self):
+        import torch.distributed as dist
+        return dist
+
+    def all_gather_rows(self, local, max_rows):
+        """all-gather a ragged [rows_r][cols] float64 block; returns list of per-rank arrays (padded rows dropped by
+        the caller, who knows each rank's count from ``owned``)."""
+        import torch
+        if self.world == 1:
+            return [local]
+        dist = self._dist()
+        cols = local.shape[1]
+        buf = np.zeros((max_rows, cols), dtype=np.float64)
+        buf[:local.shape[0]] = local
+        t = torch.from_numpy(buf)
+        if self.device is not None:
+            t = t.to(self.device, non_blocking=False)
+        out = torch.empty((self.world, max_rows, cols), dtype=torch.float64, device=t.device)
+        try:
+            dist.all_gather_into_tensor(out.view(-1), t.view(-1))
+        except (RuntimeError, AttributeError):
+            parts = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(parts, t)
+            out = torch.stack(parts, 0)
+        out = out.cpu().numpy()
+        return [out[r] for r in range(self.world)]
+
+    def all_reduce_max(self, value):
+        import torch
+        if self.world == 1:
+            return float(value)
+        t = torch.tensor([float(value)], dtype=torch.float64, device=self.device if self.device is not None else "cpu")
+        self._dist().all_reduce(t, op=self._dist().ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier(self):
+        if self.world > 1:
+            self._dist().barrier()
+
+
+def _record(c, hist_before):
+    al = c.alpha_local_step
+    lam = complex(c.lambda_k) if c.lambda_k is not None else complex(0.0, 0.0)
+    return [lam.real, lam.imag, float(c.residual_k), float(c.prev_residual), complex(al).real,
+            1.0 if isinstance(al, (complex, np.complexfloating)) else 0.0, float(c.stuck_counter),
+            float(c.local_psi_retries_needed), float(c.num_resets), float(c.w_k), float(c.state.value),
+            float(len(c.residual_history) - hist_before)]
+
+
+def _apply_record(c, rec, vec, eigen, State):
+    if eigen:
+        c.lambda_k = np.complex128(complex(rec[0], rec[1]))
+        c.v_k = vec
+    else:
+        c.x_k = vec
+    c.residual_k = np.float64(rec[2])
+    c.prev_residual = rec[3]
+    c.alpha_local_step = np.complex128(rec[4]) if rec[5] else float(rec[4])
+    c.stuck_counter = int(rec[6])
+    c.local_psi_retries_needed = int(rec[7])
+    c.num_resets = int(rec[8])
+    c.w_k = float(rec[9])
+    c.state = State(int(rec[10]))
+    for _ in range(int(rec[11])):
+        c.param_history.append(c.get_current_solution_params())
+        c.residual_history.append(c.residual_k)
+
+
+def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, engine, shard):
+    """Sharded equivalent of the loop AMS:574-576: each rank steps the live candidates it owns on its GPU, then one
+    all-gather brings every replica of the population up to date.  Returns the number of live candidates."""
+    if shard.world == 1:
+        return step_population(candidates, M, b, strat_params, problem_knowledge, engine)
+    if not candidates:
+        return 0
+    State = type(candidates[0]).State
+    live = [c for c in candidates if c.state not in (State.CONVERGED, State.RETIRED)]
+    if not live:
+        return 0
+    n = live[0].N_diag
+    eigen = live[0].problem_type.value == _abi.EIGENVALUE
+    counts = [len(range(r, len(live), shard.world)) for r in range(shard.world)]
+    mine = [live[i] for i in shard.owned(len(live))]
+    hist_before = [len(c.residual_history) for c in mine]
+    if mine:
+        step_population(mine, M, b, strat_params, problem_knowledge, engine)
+    # record + vector travel together as one float64 row: [NREC | 2n]
+    local = np.zeros((len(mine), NREC + 2 * n), dtype=np.float64)
+    for k, c in enumerate(mine):
+        local[k, :NREC] = _record(c, hist_before[k])
+        vec = c.v_k if eigen else c.x_k
+        local[k, NREC:] = np.ascontiguousarray(vec, dtype=np.complex128).view(np.float64)
+    gathered = shard.all_gather_rows(local, max(counts))
+    for r in range(shard.world):
+        if r == shard.rank:
+            continue
+        for k, i in enumerate(range(r, len(live), shard.world)):
+            row = gathered[r][k]
+            vec = row[NREC:].copy().view(np.complex128)
+            _apply_record(live[i], row[:NREC], vec, eigen, State)
+    return len(live)
+
+
+def gather_energy_and_best(shard, resid, lam, vectors, best_index=None):
+    """The per-generation exchange of the benchmark loop: all-gather (residual, lambda) of every candidate and the
+    arg-min-residual eigenpair.  resid [C] f64, lam [C] c128, vectors [C][n] c128 (host).  Returns
+    (all_resid [G*C], all_lam [G*C], best_vec [n], best_rank)."""
+    C_ = resid.shape[0]
+    n = vectors.shape[1]
+    k = (int(np.argmin(resid)) if C_ else 0) if best_index is None else int(best_index)
+    local = np.zeros((1, 3 * C_ + 2 * n), dtype=np.float64)
+    local[0, :C_] = resid
+    local[0, C_:3 * C_] = np.ascontiguousarray(lam, dtype=np.complex128).view(np.float64)
+    local[0, 3 * C_:] = vectors[k].view(np.float64)
+    rows = shard.all_gather_rows(local, 1)
+    all_resid = np.concatenate([r[0, :C_] for r in rows])
+    all_lam = np.concatenate([r[0, C_:3 * C_].copy().view(np.complex128) for r in rows])
+    best_rank = int(np.argmin([r[0, :C_].min() for r in rows]))
+    best_vec = rows[best_rank][0, 3 * C_:].copy().view(np.complex128)
+    return all_resid, all_lam, best_vec, best_rank

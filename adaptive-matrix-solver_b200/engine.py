@@ -75,6 +75,11 @@ class MausEngine:
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     @property
+    def stream_ptr(self):
+        """cudaStream_t of the context (int), e.g. for torch.cuda.ExternalStream"""
+        return int(self._lib.maus_stream(self._h) or 0)
+
+    @property
     def launches(self):
         return int(self._lib.maus_launch_count(self._h))
 
@@ -140,6 +145,11 @@ class MausEngine:
     def download_vectors(self, C_, out=None):
         out = np.empty((C_, self.n), dtype=_c128) if out is None else out
         self._check(self._lib.maus_download_vectors(self._h, int(C_), _dp(out)))
+        return out
+
+    def download_vector_range(self, first, count=1):
+        out = np.empty((count, self.n), dtype=_c128)
+        self._check(self._lib.maus_download_vector_range(self._h, int(first), int(count), _dp(out)))
         return out
 
     # -- granular pieces --------------------------------------------------------------------------------------

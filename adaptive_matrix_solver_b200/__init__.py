@@ -11,3 +11,4 @@ from ._abi import load_library, library_path, MausError          # noqa: E402,F4
 from .engine import MausEngine                                   # noqa: E402,F401
 from .solver import GpuInverseIterateSolver                      # noqa: E402,F401
 from .population import step_population, install_dropin          # noqa: E402,F401
+from .candidates import Candidate, ProblemType                   # noqa: E402,F401

@@ -92,6 +92,8 @@ int maus_set_rhs(maus_ctx* ctx, const double* b);
 /* copy C candidate vectors (v_k for eigen, x_k for linear; AMS:120) to / from the device-resident population. */
 int maus_upload_vectors(maus_ctx* ctx, int64_t C, const double* V);
 int maus_download_vectors(maus_ctx* ctx, int64_t C, double* V);
+/* `count` resident vectors starting at candidate `first` (e.g. the arg-min-residual eigenvector of a generation) */
+int maus_download_vector_range(maus_ctx* ctx, int64_t first, int64_t count, double* V);
 
 /* ---- granular pieces (the host keeps the control flow of AMS:39-104 / 145-331) ---------------------------- */
 /* Rayleigh quotient lambda_c = <v,Av>/<v,v> (lambda = 0 when |<v,v>| < 1e-12) and <v,v>, AMS:264-268.
