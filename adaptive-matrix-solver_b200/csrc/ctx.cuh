@@ -83,7 +83,7 @@ int prof_begin(maus_ctx* ctx, int kind, double work);
 void prof_end(maus_ctx* ctx, int handle);
 
 // Y[c] = A(slot) * V[c] for C candidates: dense -> DMMA GEMM (C > 8) or HBM-bound GEMV; sparse -> CSR SpMM
-int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, cplx* Y, long long C);
+int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cplx* Y, long long ldy, long long C);
 
 // batched LU solve of C systems (chunked to the workspace): X[c] = (A - sigma_c I + psi_c I + R_c)^-1 rhs_c
 int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* psi, const unsigned long long* keys,
@@ -92,5 +92,5 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
 // batched GMRES (gmres.cu)
 int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* psi, const unsigned long long* keys,
                      const unsigned char* use_jacobi, const cplx* rhs, long long rhs_stride, cplx* X, int* status,
-                     int* iters);
+                     int* iters, double max_psi_host);
 void maus_gmres_free(maus_ctx* ctx);

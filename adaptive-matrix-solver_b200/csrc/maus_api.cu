@@ -253,8 +253,17 @@ extern "C" int maus_set_dense(maus_ctx* ctx, int slot, int64_t n, const double* 
     if (!s.cm) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.cm, bytes));
     MAUS_CUDA(ctx, cudaMemcpyAsync(s.rm, A_rowmajor, bytes, cudaMemcpyHostToDevice, ctx->stream));
     MAUS_CUDA(ctx, vec_rowmajor_to_colmajor(s.rm, s.cm, (int)n, ctx->stream));
-    ctx->launches += 1;
-    MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!s.diag) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.diag, (size_t)n * sizeof(cplx)));
+    {
+        double* amax_dev = nullptr;
+        MAUS_CUDA(ctx, cudaMalloc(&amax_dev, sizeof(double)));
+        MAUS_CUDA(ctx, cudaMemsetAsync(amax_dev, 0, sizeof(double), ctx->stream));
+        MAUS_CUDA(ctx, vec_diag_amax(s.rm, (int)n, s.diag, amax_dev, ctx->stream));
+        MAUS_CUDA(ctx, cudaMemcpyAsync(&s.amax, amax_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(amax_dev);
+    }
+    ctx->launches += 2;
     s.dense = true;
     if (slot == 1) ctx->slot1_set = true;
     return MAUS_OK;
@@ -357,21 +366,21 @@ extern "C" int maus_download_vector_range(maus_ctx* ctx, int64_t first, int64_t 
 // ------------------------------------------------------------------------------------------------------------
 // matrix application
 // ------------------------------------------------------------------------------------------------------------
-int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, cplx* Y, long long C) {
+int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cplx* Y, long long ldy, long long C) {
     if (slot == 1 && !ctx->slot1_set) slot = 0;
     MatrixSlot& s = ctx->slot[slot];
     const long long n = ctx->n;
     if (s.dense) {
         if (C <= 8) {
             int h = prof_begin(ctx, 1, (double)((C + 3) / 4) * 16.0 * n * n + 32.0 * n * C);
-            MAUS_CUDA(ctx, vec_gemv_rowmajor(s.rm, V, Y, (int)n, (int)C, ctx->stream));
+            MAUS_CUDA(ctx, vec_gemv_rowmajor(s.rm, V, ldv, Y, ldy, (int)n, (int)C, ctx->stream));
             prof_end(ctx, h);
             ctx->launches += (C + 3) / 4;
         } else {
             ZgemmParams p;
             p.A = s.cm; p.lda = n; p.strideA = 0;
-            p.B = V; p.ldb = n; p.strideB = 0;
-            p.C = Y; p.ldc = n; p.strideC = 0;
+            p.B = V; p.ldb = ldv; p.strideB = 0;
+            p.C = Y; p.ldc = ldy; p.strideC = 0;
             p.M = (int)n; p.N = (int)C; p.K = (int)n; p.batch = 1; p.beta = 0; p.negate = 0;
             MAUS_CUDA(ctx, zgemm_dmma_launch(p, ctx->stream));
             ctx->launches += 1;
@@ -380,7 +389,7 @@ int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, cplx* Y, long long
     }
     if (s.sparse) {
         int h = prof_begin(ctx, 1, (double)((C + 3) / 4) * (20.0 * s.nnz + 8.0 * (n + 1)) + 32.0 * n * C);
-        MAUS_CUDA(ctx, csr_spmm(s.rowptr, s.colidx, s.vals, V, Y, n, (int)C, ctx->stream));
+        MAUS_CUDA(ctx, csr_spmm(s.rowptr, s.colidx, s.vals, V, ldv, Y, ldy, n, (int)C, ctx->stream));
         prof_end(ctx, h);
         ctx->launches += (C + 3) / 4;
         return MAUS_OK;
@@ -482,7 +491,7 @@ extern "C" int maus_rq(maus_ctx* ctx, int64_t C, const double* V, double* lambda
     const long long n = ctx->n;
     cudaStream_t st = ctx->stream;
     if (V) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->V, V, (size_t)C * n * sizeof(cplx), cudaMemcpyHostToDevice, st));
-    if ((rc = maus_apply_matrix(ctx, 0, ctx->V, ctx->Y, C))) return rc;
+    if ((rc = maus_apply_matrix(ctx, 0, ctx->V, n, ctx->Y, n, C))) return rc;
     MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, nullptr, st));
     ctx->launches += 1;
     if (lambda_out) MAUS_CUDA(ctx, cudaMemcpyAsync(lambda_out, ctx->lambda, (size_t)C * sizeof(cplx), cudaMemcpyDeviceToHost, st));
@@ -492,14 +501,14 @@ extern "C" int maus_rq(maus_ctx* ctx, int64_t C, const double* V, double* lambda
 }
 
 static int solve_device(maus_ctx* ctx, long long C, int method, const cplx* rhs, long long rhs_stride, const cplx* Rcm,
-                        bool have_keys) {
+                        bool have_keys, double max_psi) {
     const unsigned long long* keys = have_keys ? ctx->keys : nullptr;   // no key = no random perturbation (sparse, AMS:47)
     // sigma / psi / keys / jac already on the device; status pre-set (0 = solve, non-zero = skip handled by caller)
     if (method == MAUS_METHOD_LU)
         return maus_lu_solve(ctx, C, ctx->sigma, ctx->psi, keys, Rcm, rhs, rhs_stride, ctx->X, ctx->status);
     if (method == MAUS_METHOD_GMRES)
         return maus_gmres_solve(ctx, C, ctx->sigma, ctx->psi, keys, ctx->jac, rhs, rhs_stride, ctx->X, ctx->status,
-                                ctx->iters);
+                                ctx->iters, max_psi);
     return maus_fail(ctx, MAUS_E_ARG, "unknown solver method");
 }
 
@@ -531,7 +540,11 @@ extern "C" int maus_solve_shifted(maus_ctx* ctx, int64_t C, const double* sigma,
         rhs = ctx->V; rstride = n;
     }
     const bool sparse = ctx->slot[0].sparse;
-    if ((rc = solve_device(ctx, C, method, rhs, rstride, nullptr, rng_key != nullptr))) return rc;
+    {
+        double max_psi = 0.0;
+        for (long long c = 0; c < C; ++c) max_psi = std::max(max_psi, std::fabs(psi[c]));
+        if ((rc = solve_device(ctx, C, method, rhs, rstride, nullptr, rng_key != nullptr, max_psi))) return rc;
+    }
     (void)sparse;
     if (X_out) MAUS_CUDA(ctx, cudaMemcpyAsync(X_out, ctx->X, (size_t)C * n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
     if (status_out) MAUS_CUDA(ctx, cudaMemcpyAsync(status_out, ctx->status, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
@@ -566,7 +579,7 @@ extern "C" int maus_solve_with_R(maus_ctx* ctx, const double* sigma, const doubl
 }
 
 static int residual_device(maus_ctx* ctx, long long C, int problem_type, int res_slot) {
-    int rc = maus_apply_matrix(ctx, res_slot, ctx->V, ctx->Y, C); if (rc) return rc;
+    int rc = maus_apply_matrix(ctx, res_slot, ctx->V, ctx->n, ctx->Y, ctx->n, C); if (rc) return rc;
     if (problem_type == MAUS_SOLVE_LINEAR_SYSTEM && !ctx->b_set) return maus_fail(ctx, MAUS_E_STATE, "rhs not set");
     MAUS_CUDA(ctx, vec_residual_finish(ctx->V, ctx->Y, (int)ctx->n, (int)C, problem_type, ctx->lambda, ctx->b, ctx->resid,
                                        ctx->stream));
@@ -645,7 +658,7 @@ extern "C" int maus_step(maus_ctx* ctx, int64_t C, int problem_type, int method,
     const cplx* rhs; long long rstride;
     if (problem_type == MAUS_EIGENVALUE) {
         // AMS:264-270: lambda = RQ(v); sigma = lambda
-        if ((rc = maus_apply_matrix(ctx, 0, ctx->V, ctx->Y, C))) return rc;
+        if ((rc = maus_apply_matrix(ctx, 0, ctx->V, n, ctx->Y, n, C))) return rc;
         MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, ctx->status, st));
         ctx->launches += 1;
         MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->sigma, ctx->lambda, (size_t)C * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
@@ -656,7 +669,11 @@ extern "C" int maus_step(maus_ctx* ctx, int64_t C, int problem_type, int method,
         MAUS_CUDA(ctx, cudaMemsetAsync(ctx->lambda, 0, (size_t)C * sizeof(cplx), st));
         rhs = ctx->b; rstride = 0;
     }
-    if ((rc = solve_device(ctx, C, method, rhs, rstride, nullptr, rng_key != nullptr))) return rc;
+    {
+        double max_psi = 0.0;
+        for (long long c = 0; c < C; ++c) max_psi = std::max(max_psi, std::fabs(psi[c]));
+        if ((rc = solve_device(ctx, C, method, rhs, rstride, nullptr, rng_key != nullptr, max_psi))) return rc;
+    }
     MAUS_CUDA(ctx, vec_mix_normalise(ctx->V, ctx->X, (int)n, (int)C, problem_type, ctx->alpha, ctx->mixnorm, ctx->status, st));
     ctx->launches += 1;
     if ((rc = residual_device(ctx, C, problem_type, res_slot))) return rc;

@@ -10,7 +10,8 @@ constexpr int SP_NT = 256, SP_LANES = 8;
 template <int CB>
 __global__ void __launch_bounds__(SP_NT) csr_spmm_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx,
                                                          const cplx* __restrict__ vals, const cplx* __restrict__ V,
-                                                         cplx* __restrict__ Y, long long n, int c0, int ncand) {
+                                                         long long ldv, cplx* __restrict__ Y, long long ldy, long long n,
+                                                         int c0, int ncand) {
     const long long row = ((long long)blockIdx.x * SP_NT + threadIdx.x) / SP_LANES;
     const int sub = threadIdx.x & (SP_LANES - 1);
     cplx acc[CB];
@@ -23,7 +24,7 @@ __global__ void __launch_bounds__(SP_NT) csr_spmm_kernel(const long long* __rest
             const int j = __ldcs(&colidx[k]);
 #pragma unroll
             for (int c = 0; c < CB; ++c)
-                if (c < ncand) cfma(acc[c], a, __ldg(&V[(long long)(c0 + c) * n + j]));
+                if (c < ncand) cfma(acc[c], a, __ldg(&V[(long long)(c0 + c) * ldv + j]));
         }
     }
 #pragma unroll
@@ -33,21 +34,21 @@ __global__ void __launch_bounds__(SP_NT) csr_spmm_kernel(const long long* __rest
             acc[c].x += __shfl_xor_sync(0xffffffffu, acc[c].x, o);
             acc[c].y += __shfl_xor_sync(0xffffffffu, acc[c].y, o);
         }
-        if (sub == 0 && row < n && c < ncand) Y[(long long)(c0 + c) * n + row] = acc[c];
+        if (sub == 0 && row < n && c < ncand) Y[(long long)(c0 + c) * ldy + row] = acc[c];
     }
 }
 
 }  // namespace
 
-cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* V, cplx* Y, long long n,
-                     int C, cudaStream_t stream) {
+cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* V, long long ldv, cplx* Y,
+                     long long ldy, long long n, int C, cudaStream_t stream) {
     const long long threads = n * SP_LANES;
     const unsigned grid = (unsigned)((threads + SP_NT - 1) / SP_NT);
     for (int c0 = 0; c0 < C; c0 += 4) {
         const int nc = (C - c0 < 4) ? (C - c0) : 4;
-        if (nc == 1) csr_spmm_kernel<1><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, Y, n, c0, nc);
-        else if (nc == 2) csr_spmm_kernel<2><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, Y, n, c0, nc);
-        else csr_spmm_kernel<4><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, Y, n, c0, nc);
+        if (nc == 1) csr_spmm_kernel<1><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, c0, nc);
+        else if (nc == 2) csr_spmm_kernel<2><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, c0, nc);
+        else csr_spmm_kernel<4><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, c0, nc);
     }
     return cudaGetLastError();
 }

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(RED_NT) nan_scan_kernel(const cplx* __restrict
 constexpr int GV_NT = 256, GV_ROWS = 16, GV_JC = 512;
 template <int CB>
 __global__ void __launch_bounds__(GV_NT) gemv_rowmajor_kernel(const cplx* __restrict__ A, const cplx* __restrict__ V,
-                                                              cplx* __restrict__ Y, int n, int c0, int ncand) {
+                                                              long long ldv, cplx* __restrict__ Y, long long ldy, int n,
+                                                              int c0, int ncand) {
     __shared__ cplx sV[CB][GV_JC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row_base = blockIdx.x * GV_ROWS;
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(GV_NT) gemv_rowmajor_kernel(const cplx* __rest
         __syncthreads();
         for (int idx = threadIdx.x; idx < CB * jc; idx += GV_NT) {
             int c = idx / jc, j = idx - c * jc;
-            sV[c][j] = (c < ncand) ? V[(long long)(c0 + c) * n + j0 + j] : cmake(0.0, 0.0);
+            sV[c][j] = (c < ncand) ? V[(long long)(c0 + c) * ldv + j0 + j] : cmake(0.0, 0.0);
         }
         __syncthreads();
 #pragma unroll
@@ -200,12 +201,32 @@ __global__ void __launch_bounds__(GV_NT) gemv_rowmajor_kernel(const cplx* __rest
 #pragma unroll
         for (int c = 0; c < CB; ++c) {
             cplx s = warp_sum(acc[r][c]);
-            if (lane == 0 && row < n && c < ncand) Y[(long long)(c0 + c) * n + row] = s;
+            if (lane == 0 && row < n && c < ncand) Y[(long long)(c0 + c) * ldy + row] = s;
         }
     }
 }
 
+__global__ void __launch_bounds__(256) diag_amax_kernel(const cplx* __restrict__ A, int n, cplx* __restrict__ diag, double* amax) {
+    const long long total = (long long)n * n;
+    double m = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        cplx a = A[i];
+        double v = fabs(a.x) + fabs(a.y);
+        if (v == v) m = fmax(m, v);
+        if (i / n == i % n) diag[i / n] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0 && isfinite(m))
+        atomicMax(reinterpret_cast<unsigned long long*>(amax), (unsigned long long)__double_as_longlong(m));   // m >= 0: bit order = value order
+}
+
 }  // namespace
+
+cudaError_t vec_diag_amax(const cplx* A_rm, int n, cplx* diag, double* amax, cudaStream_t stream) {
+    diag_amax_kernel<<<MAUS_SM_COUNT_B200 * 4, 256, 0, stream>>>(A_rm, n, diag, amax);
+    return cudaGetLastError();
+}
 
 cudaError_t vec_rowmajor_to_colmajor(const cplx* in_rm, cplx* out_cm, int n, cudaStream_t stream) {
     dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 32);
@@ -235,13 +256,14 @@ cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int 
     return cudaGetLastError();
 }
 
-cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, cplx* Y, int n, int C, cudaStream_t stream) {
+cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
+                              cudaStream_t stream) {
     const int grid = (n + GV_ROWS - 1) / GV_ROWS;
     for (int c0 = 0; c0 < C; c0 += 4) {
         const int nc = (C - c0 < 4) ? (C - c0) : 4;
-        if (nc == 1) gemv_rowmajor_kernel<1><<<grid, GV_NT, 0, stream>>>(A_rm, V, Y, n, c0, nc);
-        else if (nc == 2) gemv_rowmajor_kernel<2><<<grid, GV_NT, 0, stream>>>(A_rm, V, Y, n, c0, nc);
-        else gemv_rowmajor_kernel<4><<<grid, GV_NT, 0, stream>>>(A_rm, V, Y, n, c0, nc);
+        if (nc == 1) gemv_rowmajor_kernel<1><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
+        else if (nc == 2) gemv_rowmajor_kernel<2><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
+        else gemv_rowmajor_kernel<4><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
     }
     return cudaGetLastError();
 }

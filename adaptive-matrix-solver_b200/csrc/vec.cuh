@@ -22,4 +22,8 @@ cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int 
                                 const cplx* b, double* resid, cudaStream_t stream);
 
 // Y[c] = A_rowmajor * V[c]: HBM-bound batched matvec, one warp per matrix row, CB candidates per pass
-cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, cplx* Y, int n, int C, cudaStream_t stream);
+cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
+                              cudaStream_t stream);
+
+// diag[i] = A[i][i]; *amax = max_ij (|re| + |im|)  (amax must be zero-initialised)
+cudaError_t vec_diag_amax(const cplx* A_rm, int n, cplx* diag, double* amax, cudaStream_t stream);
