@@ -1,0 +1,46 @@
+"""CPU stand-in for MausEngine used ONLY by the world_size-2 gloo tests of the host-side sharding logic (there is no
+GPU in the CPU test tier).  Numerics come from the oracle; it mimics the subset of the engine API step_population uses."""
+import numpy as np
+import scipy.linalg as sla
+
+from oracle import maus_oracle as mo
+
+
+class FakeEngine:
+    def __init__(self):
+        self.n = 0
+        self.is_sparse = False
+        self.generation = 0
+        self.A = [None, None]
+        self.b = None
+        self.calls = 0
+
+    def set_matrix(self, A, slot=0):
+        self.A[slot] = np.asarray(A, dtype=np.complex128)
+        if slot == 0:
+            self.n = self.A[0].shape[0]
+            self.A[1] = None
+
+    def set_rhs(self, b):
+        self.b = np.asarray(b, dtype=np.complex128)
+
+    def step(self, problem_type, alpha, psi, V=None, rng_key=None, method=0, use_jacobi=None, res_slot=0, out=None):
+        C_ = len(alpha)
+        A = self.A[0]
+        Ares = self.A[res_slot] if self.A[res_slot] is not None else A
+        lam = np.zeros(C_, dtype=np.complex128); resid = np.zeros(C_); mixn = np.zeros(C_)
+        status = np.zeros(C_, dtype=np.int32); iters = np.zeros(C_, dtype=np.int32)
+        for c in range(C_):
+            if problem_type == 1:
+                lam[c] = mo.rayleigh_quotient(A, V[c])
+                x = mo.shifted_solve_dense(A, lam[c], psi[c], V[c])
+                v2, nv = mo.mix_normalise(V[c], x, alpha[c])
+                V[c] = v2; mixn[c] = nv
+                resid[c] = mo.residual_eigen(Ares, V[c], lam[c])
+            else:
+                x = sla.solve(A + psi[c] * np.eye(self.n), self.b)
+                V[c] = (1.0 - alpha[c]) * V[c] + alpha[c] * x
+                resid[c] = mo.residual_linear(Ares, V[c], self.b)
+        self.generation += 1
+        self.calls += 1
+        return dict(lam=lam, resid=resid, mixnorm=mixn, status=status, iters=iters)
