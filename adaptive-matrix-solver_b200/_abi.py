@@ -17,7 +17,7 @@ EXPORTS = [
     "maus_create", "maus_destroy", "maus_last_error", "maus_set_workspace_limit", "maus_info", "maus_alloc_pinned",
     "maus_free_pinned", "maus_set_dense", "maus_set_csc", "maus_set_rhs", "maus_upload_vectors",
     "maus_download_vectors", "maus_download_vector_range", "maus_rq", "maus_solve_shifted", "maus_solve_with_R", "maus_mix_residual",
-    "maus_residual", "maus_step", "maus_launch_count", "maus_profile_reset", "maus_profile_read", "maus_stream", "maus_debug_zgemm",
+    "maus_residual", "maus_step", "maus_launch_count", "maus_profile_reset", "maus_profile_read", "maus_profile_read_kind", "maus_stream", "maus_debug_zgemm",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library():
         "maus_launch_count": (i64, [vp]),
         "maus_profile_reset": (i32, [vp, i32]),
         "maus_profile_read": (i32, [vp, dp, i64p, dp, dp, i64p, dp]),
+        "maus_profile_read_kind": (i32, [vp, i32, dp, i64p, dp]),
         "maus_stream": (vp, [vp]),
         "maus_debug_zgemm": (i32, [vp, i32, i32, i32, i32, dp, dp, dp, i32, i32, i32]),
     }

@@ -23,11 +23,11 @@ struct MatrixSlot {
 struct ProfAccum {
     bool enabled = false;
     std::vector<cudaEvent_t> ev;     // pairs
-    std::vector<int> kind;           // 0 = LU trailing GEMM, 1 = matvec
+    std::vector<int> kind;           // MAUS_PROF_* (include/maus_b200.h)
     size_t used = 0;
-    double ms[2] = {0.0, 0.0};
-    long long launches[2] = {0, 0};
-    double work[2] = {0.0, 0.0};     // flops (kind 0) / bytes (kind 1)
+    double ms[8] = {0};
+    long long launches[8] = {0};
+    double work[8] = {0};            // flops (GEMM kinds) / bytes (HBM kinds)
 };
 
 struct maus_ctx {

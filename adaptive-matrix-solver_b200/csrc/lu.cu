@@ -99,95 +99,114 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
 
     for (int ib0 = 0; ib0 < jb; ib0 += IB) {
         const int ibw = min(IB, jb - ib0);
+        // a[q][i] always holds column (current j) + i of row q: after every column the window is shifted left by one,
+        // so the column loop below is a ROLLED loop with constant register indices (the unrolled version was 480 KB of
+        // SASS and instruction-fetch bound)
         cplx a[R][IB];
-        bool live[R];     // rows that were not yet pivots when this inner block started
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-            live[q] = valid[q] && !done[q];
+            const bool live = valid[q] && !done[q];
 #pragma unroll
-            for (int j = 0; j < IB; ++j)
-                a[q][j] = (live[q] && j < ibw) ? P[row[q] + (long long)(ib0 + j) * ld] : cmake(0.0, 0.0);
+            for (int i = 0; i < IB; ++i)
+                a[q][i] = (live && i < ibw) ? P[row[q] + (long long)(ib0 + i) * ld] : cmake(0.0, 0.0);
         }
+#pragma unroll 1
+        for (int j = 0; j < ibw; ++j) {
+            // ---- pivot search: thread -> warp -> CTA -> cluster ----
+            double bv = -1.0; int br = 0x7fffffff;
 #pragma unroll
-        for (int j = 0; j < IB; ++j) {
-            if (j < ibw) {
-                // ---- pivot search: thread -> warp -> CTA -> cluster ----
-                double bv = -1.0; int br = 0x7fffffff;
-#pragma unroll
-                for (int q = 0; q < R; ++q)
-                    if (valid[q] && !done[q]) {
-                        double v = cabs1(a[q][j]);
-                        if (v != v) v = INFINITY;
-                        if (v > bv || (v == bv && row[q] < br)) { bv = v; br = row[q]; }
-                    }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    int orow = __shfl_xor_sync(0xffffffffu, br, o);
-                    if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; }
+            for (int q = 0; q < R; ++q)
+                if (valid[q] && !done[q]) {
+                    double v = cabs1(a[q][0]);
+                    if (v != v) v = INFINITY;
+                    if (v > bv || (v == bv && row[q] < br)) { bv = v; br = row[q]; }
                 }
-                if (lane == 0) { wval[warp] = bv; wrow[warp] = br; }
-                __syncthreads();
-                double cv = -1.0; int cr = 0x7fffffff;
 #pragma unroll
-                for (int w = 0; w < PANEL_NT / 32; ++w) {
-                    double ov = wval[w]; int orow = wrow[w];
-                    if (ov > cv || (ov == cv && orow < cr)) { cv = ov; cr = orow; }
-                }
-                // the owner of the CTA's best row publishes it into every CTA's slot[rank]
-                if (cv >= 0.0) {
-#pragma unroll
-                    for (int q = 0; q < R; ++q)
-                        if (valid[q] && !done[q] && row[q] == cr) {
-                            cplx rc = crecip(a[q][j]);
-                            for (int d = 0; d < NC; ++d) {
-                                PanelSlot<IB>* s = cluster.map_shared_rank(&slots[j & 1][rank], d);
-                                s->val = cv; s->row = cr; s->recip = rc;
-#pragma unroll
-                                for (int jj = 0; jj < IB; ++jj) s->data[jj] = a[q][jj];
-                            }
-                        }
-                } else if (threadIdx.x == 0) {
-                    for (int d = 0; d < NC; ++d) {
-                        PanelSlot<IB>* s = cluster.map_shared_rank(&slots[j & 1][rank], d);
-                        s->val = -1.0; s->row = 0x7fffffff;
-                    }
-                }
-                cluster.sync();
-                double wv = -1.0; int wr = 0x7fffffff, wi = 0;
-                for (int d = 0; d < NC; ++d) {
-                    double ov = slots[j & 1][d].val; int orow = slots[j & 1][d].row;
-                    if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wi = d; }
-                }
-                const PanelSlot<IB>& ws = slots[j & 1][wi];
-                if (threadIdx.x < IB) L11[j][threadIdx.x] = ws.data[threadIdx.x];
-                if (threadIdx.x == 0) piv[ib0 + j] = wr;
-                const bool zero = !(wv > 0.0);
-                if (zero && !zero_seen) { zero_seen = true; zero_col = k0 + ib0 + j + 1; }
-                const cplx rc = ws.recip;
-#pragma unroll
-                for (int q = 0; q < R; ++q)
-                    if (valid[q] && !done[q]) {
-                        if (row[q] == wr) done[q] = true;
-                        else if (!zero) {
-                            cplx l = cmul(a[q][j], rc);
-                            a[q][j] = l;
-#pragma unroll
-                            for (int jj = j + 1; jj < IB; ++jj) cfms(a[q][jj], l, ws.data[jj]);
-                        }
-                    }
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                int orow = __shfl_xor_sync(0xffffffffu, br, o);
+                if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; }
             }
+            if (lane == 0) { wval[warp] = bv; wrow[warp] = br; }
+            __syncthreads();
+            double cv = -1.0; int cr = 0x7fffffff;
+#pragma unroll
+            for (int w = 0; w < PANEL_NT / 32; ++w) {
+                double ov = wval[w]; int orow = wrow[w];
+                if (ov > cv || (ov == cv && orow < cr)) { cv = ov; cr = orow; }
+            }
+            // the warp that owns the CTA's best row publishes it into every CTA's slot[rank]: the owner lane broadcasts
+            // its window by shuffles, then the 32 lanes spread the remote (DSMEM) stores
+            if (cv >= 0.0) {
+                const int owner_t = (cr % T) - rank * PANEL_NT;      // thread of this CTA that holds row cr
+                const int owner_q = cr / T;
+                if (warp == (owner_t >> 5)) {
+                    const int ol = owner_t & 31;
+                    cplx keep = cmake(0.0, 0.0), rc = cmake(0.0, 0.0);
+                    const int e = lane % IB;
+#pragma unroll
+                    for (int i = 0; i < IB; ++i) {
+                        cplx sel = a[0][i];
+#pragma unroll
+                        for (int q = 1; q < R; ++q) if (owner_q == q) sel = a[q][i];
+                        if (i == 0) {
+                            if (lane == ol) rc = crecip(sel);
+                            rc.x = __shfl_sync(0xffffffffu, rc.x, ol); rc.y = __shfl_sync(0xffffffffu, rc.y, ol);
+                        }
+                        double vx = __shfl_sync(0xffffffffu, sel.x, ol), vy = __shfl_sync(0xffffffffu, sel.y, ol);
+                        if (i == e) keep = cmake(vx, vy);
+                    }
+                    for (int d = lane / IB; d < NC; d += 32 / IB) {
+                        PanelSlot<IB>* s = cluster.map_shared_rank(&slots[j & 1][rank], d);
+                        s->data[e] = keep;
+                        if (e == 0) { s->val = cv; s->row = cr; s->recip = rc; }
+                    }
+                }
+            } else if (threadIdx.x == 0) {
+                for (int d = 0; d < NC; ++d) {
+                    PanelSlot<IB>* s = cluster.map_shared_rank(&slots[j & 1][rank], d);
+                    s->val = -1.0; s->row = 0x7fffffff;
+                }
+            }
+            cluster.sync();
+            double wv = -1.0; int wr = 0x7fffffff, wi = 0;
+            for (int d = 0; d < NC; ++d) {
+                double ov = slots[j & 1][d].val; int orow = slots[j & 1][d].row;
+                if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wi = d; }
+            }
+            const PanelSlot<IB>& ws = slots[j & 1][wi];
+            if (threadIdx.x == 0) piv[ib0 + j] = wr;
+            const bool zero = !(wv > 0.0);
+            if (zero && !zero_seen) { zero_seen = true; zero_col = k0 + ib0 + j + 1; }
+            const cplx rc = ws.recip;
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                if (valid[q] && !done[q]) {
+                    cplx* prow = P + row[q] + (long long)(ib0 + j) * ld;
+                    if (row[q] == wr) {
+                        done[q] = true;                               // my window holds U(j, j..): final values
+#pragma unroll
+                        for (int i = 0; i < IB; ++i)
+                            if (j + i < ibw) prow[(long long)i * ld] = a[q][i];
+                    } else {
+                        cplx l = zero ? a[q][0] : cmul(a[q][0], rc);
+                        prow[0] = l;                                   // multiplier, stays in its physical row
+                        if (zero) l = cmake(0.0, 0.0);
+#pragma unroll
+                        for (int i = 0; i + 1 < IB; ++i) { cplx x = a[q][i + 1]; cfms(x, l, ws.data[i + 1]); a[q][i] = x; }
+                        a[q][IB - 1] = cmake(0.0, 0.0);
+                    }
+                }
         }
-        // write the inner block back (multipliers / U entries stay in their physical rows)
-#pragma unroll
-        for (int q = 0; q < R; ++q)
-            if (live[q])
-#pragma unroll
-                for (int j = 0; j < IB; ++j)
-                    if (j < ibw) P[row[q] + (long long)(ib0 + j) * ld] = a[q][j];
-        __syncthreads();   // L11 / piv complete in this CTA
         const int rest = jb - (ib0 + ibw);
         if (rest > 0) {
+            cluster.sync();     // multipliers / U entries written in the column loop are visible cluster-wide
+            // L11 = multipliers of the block's pivot rows w.r.t. the earlier pivots of the block
+            for (int idx = threadIdx.x; idx < IB * IB; idx += PANEL_NT) {
+                const int jj = idx / IB, i = idx % IB;
+                if (i < jj && jj < ibw) L11[jj][i] = __ldcg(&P[piv[ib0 + jj] + (long long)(ib0 + i) * ld]);
+            }
+            __syncthreads();
             // (i) U12 block = L11^-1 * (pivot rows, remaining panel columns); every CTA computes its own copy
             if ((int)threadIdx.x < rest) {
                 const int c = threadIdx.x;
@@ -203,22 +222,44 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
                 const long long coff = (long long)(ib0 + ibw + threadIdx.x) * ld;
                 for (int j = 0; j < ibw; ++j) P[piv[ib0 + j] + coff] = U12[j][threadIdx.x];
             }
-            // (ii) rank-ibw update of the remaining panel columns for the rows that are still live
+            // (ii) rank-ibw update of the remaining panel columns for the rows that are still live: four columns at a
+            // time (independent FMA chains), the next four prefetched while the current ones are updated
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 if (valid[q] && !done[q]) {
+                    cplx l[IB];
+#pragma unroll
+                    for (int j = 0; j < IB; ++j) l[j] = (j < ibw) ? P[row[q] + (long long)(ib0 + j) * ld] : cmake(0.0, 0.0);
                     cplx* prow = P + row[q] + (long long)(ib0 + ibw) * ld;
-                    for (int c = 0; c < rest; ++c) {
+                    const int rest4 = rest & ~3;
+                    cplx nx0, nx1, nx2, nx3;
+                    if (rest4 > 0) { nx0 = prow[0]; nx1 = prow[(long long)ld]; nx2 = prow[2LL * ld]; nx3 = prow[3LL * ld]; }
+#pragma unroll 1
+                    for (int c = 0; c < rest4; c += 4) {
+                        cplx x0 = nx0, x1 = nx1, x2 = nx2, x3 = nx3;
+                        if (c + 4 < rest4) {
+                            nx0 = prow[(long long)(c + 4) * ld]; nx1 = prow[(long long)(c + 5) * ld];
+                            nx2 = prow[(long long)(c + 6) * ld]; nx3 = prow[(long long)(c + 7) * ld];
+                        }
+#pragma unroll
+                        for (int j = 0; j < IB; ++j) {
+                            cfms(x0, l[j], U12[j][c]); cfms(x1, l[j], U12[j][c + 1]);
+                            cfms(x2, l[j], U12[j][c + 2]); cfms(x3, l[j], U12[j][c + 3]);
+                        }
+                        prow[(long long)c * ld] = x0; prow[(long long)(c + 1) * ld] = x1;
+                        prow[(long long)(c + 2) * ld] = x2; prow[(long long)(c + 3) * ld] = x3;
+                    }
+                    for (int c = rest4; c < rest; ++c) {
                         cplx x = prow[(long long)c * ld];
 #pragma unroll
-                        for (int j = 0; j < IB; ++j)
-                            if (j < ibw) cfms(x, a[q][j], U12[j][c]);
+                        for (int j = 0; j < IB; ++j) cfms(x, l[j], U12[j][c]);
                         prow[(long long)c * ld] = x;
                     }
                 }
+            // Updates written in (ii) are read by other CTAs in the next block's step (i): the column loop of the next
+            // block contains cluster barriers (release/acquire) before that read, and the reads use ld.cg.
+            __syncthreads();   // U12 / L11 are rewritten by the next block
         }
-        // Updates written in (ii) are read by other CTAs in the next block's step (i): the column loop of the next
-        // block contains at least one cluster barrier (release/acquire) before that read, and the reads use ld.cg.
     }
     __syncthreads();
     // ---- net row permutation of this panel (relative to k0) ----

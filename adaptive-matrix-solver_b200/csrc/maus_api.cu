@@ -212,7 +212,7 @@ extern "C" int maus_profile_reset(maus_ctx* ctx, int enable) {
     ProfAccum& pr = ctx->prof;
     pr.enabled = enable != 0;
     pr.used = 0;
-    pr.ms[0] = pr.ms[1] = 0.0; pr.launches[0] = pr.launches[1] = 0; pr.work[0] = pr.work[1] = 0.0;
+    for (int k = 0; k < 8; ++k) { pr.ms[k] = 0.0; pr.launches[k] = 0; pr.work[k] = 0.0; }
     return MAUS_OK;
 }
 
@@ -233,6 +233,16 @@ extern "C" int maus_profile_read(maus_ctx* ctx, double* lu_gemm_ms, int64_t* lu_
     if (matvec_ms) *matvec_ms = pr.ms[1];
     if (matvec_launches) *matvec_launches = pr.launches[1];
     if (matvec_bytes) *matvec_bytes = pr.work[1];
+    return MAUS_OK;
+}
+
+extern "C" int maus_profile_read_kind(maus_ctx* ctx, int kind, double* ms, int64_t* launches, double* work) {
+    if (!ctx || kind < 0 || kind >= 8) return MAUS_E_ARG;
+    int rc = maus_profile_read(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (ms) *ms = ctx->prof.ms[kind];
+    if (launches) *launches = ctx->prof.launches[kind];
+    if (work) *work = ctx->prof.work[kind];
     return MAUS_OK;
 }
 
@@ -372,23 +382,25 @@ int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cpl
     const long long n = ctx->n;
     if (s.dense) {
         if (C <= 8) {
-            int h = prof_begin(ctx, 1, (double)((C + 3) / 4) * 16.0 * n * n + 32.0 * n * C);
+            int h = prof_begin(ctx, MAUS_PROF_MATVEC, (double)((C + 3) / 4) * 16.0 * n * n + 32.0 * n * C);
             MAUS_CUDA(ctx, vec_gemv_rowmajor(s.rm, V, ldv, Y, ldy, (int)n, (int)C, ctx->stream));
             prof_end(ctx, h);
             ctx->launches += (C + 3) / 4;
         } else {
-            ZgemmParams p;
+            ZgemmParams p = {};
             p.A = s.cm; p.lda = n; p.strideA = 0;
             p.B = V; p.ldb = ldv; p.strideB = 0;
             p.C = Y; p.ldc = ldy; p.strideC = 0;
             p.M = (int)n; p.N = (int)C; p.K = (int)n; p.batch = 1; p.beta = 0; p.negate = 0;
+            int h = prof_begin(ctx, MAUS_PROF_MATVEC_GEMM, 8.0 * n * (double)n * C);
             MAUS_CUDA(ctx, zgemm_dmma_launch(p, ctx->stream));
+            prof_end(ctx, h);
             ctx->launches += 1;
         }
         return MAUS_OK;
     }
     if (s.sparse) {
-        int h = prof_begin(ctx, 1, (double)((C + 3) / 4) * (20.0 * s.nnz + 8.0 * (n + 1)) + 32.0 * n * C);
+        int h = prof_begin(ctx, MAUS_PROF_MATVEC, (double)((C + 3) / 4) * (20.0 * s.nnz + 8.0 * (n + 1)) + 32.0 * n * C);
         MAUS_CUDA(ctx, csr_spmm(s.rowptr, s.colidx, s.vals, V, ldv, Y, ldy, n, (int)C, ctx->stream));
         prof_end(ctx, h);
         ctx->launches += (C + 3) / 4;
@@ -435,25 +447,33 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
     cudaStream_t st = ctx->stream;
     for (long long c0 = 0; c0 < C; c0 += wb) {
         const int nb = (int)std::min<long long>(wb, C - c0);
+        int hb = prof_begin(ctx, MAUS_PROF_BUILD, 16.0 * n * (double)n * (nb + 1));
         MAUS_CUDA(ctx, lu_build_aug(ctx->W, strideW, n, nb, s.cm, sigma + c0, psi + c0, keys ? keys + c0 : nullptr, Rcm,
                                     rhs + c0 * rhs_stride, rhs_stride, st));
+        prof_end(ctx, hb);
         MAUS_CUDA(ctx, cudaMemsetAsync(ctx->info, 0, (size_t)nb * sizeof(int), st));
         ctx->launches += 1;
         for (int k0 = 0; k0 < n; k0 += LU_NB) {
             const int jb = std::min(LU_NB, n - k0);
+            int hp = prof_begin(ctx, MAUS_PROF_PANEL, 8.0 * (n - k0) * (double)jb * jb * 0.5 * nb);
             MAUS_CUDA(ctx, lu_panel(ctx->W, strideW, n, k0, jb, nb, ctx->pairs, ctx->info, st));
+            prof_end(ctx, hp);
+            hp = prof_begin(ctx, MAUS_PROF_PERMUTE, 0.0);
             MAUS_CUDA(ctx, lu_permute_rows(ctx->W, strideW, n, k0, nb, ctx->pairs, st));
+            prof_end(ctx, hp);
             ctx->launches += 2;
             const int ncols = n + 1 - (k0 + jb);       // trailing columns incl. the rhs column
             if (ncols <= 0) continue;
+            hp = prof_begin(ctx, MAUS_PROF_TRTRI, 0.0);
             MAUS_CUDA(ctx, lu_trtri(ctx->W, strideW, n, k0, jb, nb, ctx->Linv, st));
-            ZgemmParams p;
+            prof_end(ctx, hp);
+            ZgemmParams p = {};
             cplx* A12 = ctx->W + (long long)(k0 + jb) * n + k0;
             p.A = ctx->Linv; p.lda = LU_NB; p.strideA = (long long)LU_NB * LU_NB;
             p.B = A12; p.ldb = n; p.strideB = strideW;
             p.C = A12; p.ldc = n; p.strideC = strideW;
             p.M = jb; p.N = ncols; p.K = jb; p.batch = nb; p.beta = 0; p.negate = 0;
-            int h = prof_begin(ctx, 0, 8.0 * jb * (double)ncols * jb * nb);
+            int h = prof_begin(ctx, MAUS_PROF_LU_GEMM, 8.0 * jb * (double)ncols * jb * nb);
             MAUS_CUDA(ctx, zgemm_dmma_launch(p, st));            // U12 = L11^-1 A12 (in place, one row tile)
             prof_end(ctx, h);
             ctx->launches += 2;
@@ -463,13 +483,15 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
                 p.B = A12;                                                                           // U12
                 p.C = ctx->W + (long long)(k0 + jb) * n + (k0 + jb);                                 // A22
                 p.M = m2; p.N = ncols; p.K = jb; p.beta = 1; p.negate = 1;
-                h = prof_begin(ctx, 0, 8.0 * m2 * (double)ncols * jb * nb);
+                h = prof_begin(ctx, MAUS_PROF_LU_GEMM, 8.0 * m2 * (double)ncols * jb * nb);
                 MAUS_CUDA(ctx, zgemm_dmma_launch(p, st));
                 prof_end(ctx, h);
                 ctx->launches += 1;
             }
         }
+        hb = prof_begin(ctx, MAUS_PROF_BACKSOLVE, 8.0 * n * (double)n * nb);
         MAUS_CUDA(ctx, lu_backsolve(ctx->W, strideW, n, nb, ctx->info, X + c0 * n, status + c0, st));
+        prof_end(ctx, hb);
         ctx->launches += 1;
     }
     return MAUS_OK;
@@ -702,7 +724,7 @@ extern "C" int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, c
     MAUS_CUDA(ctx, cudaMemcpyAsync(dA, A, ba, cudaMemcpyHostToDevice, st));
     MAUS_CUDA(ctx, cudaMemcpyAsync(dB, B, bb, cudaMemcpyHostToDevice, st));
     MAUS_CUDA(ctx, cudaMemcpyAsync(dC, Cm, bc, cudaMemcpyHostToDevice, st));
-    ZgemmParams p;
+    ZgemmParams p = {};
     p.A = dA; p.lda = M; p.strideA = (long long)M * K;
     p.B = dB; p.ldb = K; p.strideB = (long long)K * N;
     p.C = dC; p.ldc = M; p.strideC = (long long)M * N;

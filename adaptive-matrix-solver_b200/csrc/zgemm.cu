@@ -10,21 +10,37 @@
 // global memory keeps numpy's complex128 layout end to end.
 //
 //   CTA tile 128 x 64 complex, 8 consumer warps (2 x 4), each 64 x 16 complex = 8 x 4 DMMA tiles (64 f64 accum),
-//   + 1 producer warp that stages K-slabs of 16 complex with cp.async.bulk (TMA bulk copies, SASS UBLKCP) into a
-//   4-deep shared-memory ring guarded by full/empty mbarriers.  Column strides in shared memory are padded
-//   (132 / 18 complex) so that both fragment loads are bank-conflict free.
+//   + 1 producer warp that stages the operands with cp.async.bulk (TMA bulk copies, SASS UBLKCP) into shared-memory
+//   rings guarded by full/empty mbarriers: A in 3 slabs of 16 complex k (2 KB copies), B in 2 slabs of 32 complex k
+//   (512 B copies -- measured: the bulk-copy path costs ~35 ns per copy per SM, so copy COUNT, not bytes, bounds the
+//   feed).  The kernel is persistent (one CTA per SM walks the tile list), the producer runs ahead across tiles and
+//   prefetches the next C tile into L2, from which the accumulators are initialised.  Column strides in shared
+//   memory are padded (132 / 34 complex) so that both fragment loads are bank-conflict free.
+#include <cstdlib>
 #include "zgemm.cuh"
 
 namespace {
 
-constexpr int TM = 128, TN = 64, KC = 16, STAGES = 4;
-constexpr int LDSA = TM + 4;     // complex elements between consecutive k-columns of the A slab
-constexpr int LDSB = KC + 2;     // complex elements between consecutive n-columns of the B slab
-constexpr int A_STAGE = KC * LDSA;           // complex elements
+constexpr int TN = 64;
+constexpr int KC = 16, STAGES = 3;           // A slabs: 16 complex k per stage (16 bulk copies of TM*16 B)
+constexpr int KCB = 32;                      // B slabs: 32 complex k per stage (64 bulk copies of 512 B) -- fewer, larger copies
+constexpr int LDSB = KCB + 2;                // complex elements between consecutive n-columns of the B slab
 constexpr int B_STAGE = TN * LDSB;
-constexpr int NCONS = 8;                     // consumer warps
-constexpr int NTHREADS = (NCONS + 1) * 32;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(cplx) + 2 * STAGES * sizeof(uint64_t);
+// Tile configurations.  AB = m8 row-blocks per warp (warp tile 8*AB x 16 complex); NWM x 4 consumer warps cover TM x 64.
+//   <128, 8>: 8 consumer warps, 1 CTA / SM, B double-buffered        <128, 4>: 16 consumer warps
+//   < 64, 8>: 4 consumer warps, 2 CTAs / SM (one CTA's C-tile epilogue and pipeline bubbles hide behind the other's MMAs)
+template <int TM_, int AB> struct Cfg {
+    static constexpr int TM = TM_;
+    static constexpr int NWM = TM / (8 * AB);
+    static constexpr int NCONS = NWM * 4;
+    static constexpr int NTHREADS = (NCONS + 1) * 32;
+    static constexpr int CTAS_PER_SM = (TM == 64) ? 2 : 1;
+    static constexpr int BSTAGES = (TM == 64) ? 1 : 2;      // 2 CTAs / SM must stay under 113 KB each
+    static constexpr int LDSA = TM + 4;      // complex elements between consecutive k-columns of the A slab
+    static constexpr int A_STAGE = KC * LDSA;
+    static constexpr int NBAR = 2 * STAGES + 2 * BSTAGES;
+    static constexpr size_t SMEM_BYTES = (size_t)(STAGES * A_STAGE + BSTAGES * B_STAGE) * sizeof(cplx) + NBAR * sizeof(uint64_t);
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -56,121 +72,178 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) zgemm_dmma_kernel(ZgemmParams p) {
+template <int TM, int AB>
+__global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_SM) zgemm_dmma_kernel(ZgemmParams p) {
+    using CF = Cfg<TM, AB>;
+    constexpr int NCONS = CF::NCONS, BSTAGES = CF::BSTAGES, LDSA = CF::LDSA, A_STAGE = CF::A_STAGE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* sA = reinterpret_cast<cplx*>(smem_raw);
     cplx* sB = sA + STAGES * A_STAGE;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + BSTAGES * B_STAGE);
     uint64_t* empty = full + STAGES;
+    uint64_t* bfull = empty + STAGES;
+    uint64_t* bempty = bfull + BSTAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN, bz = blockIdx.z;
-    const cplx* A = p.A + (long long)bz * p.strideA;
-    const cplx* B = p.B + (long long)bz * p.strideB;
-    cplx* C = p.C + (long long)bz * p.strideC;
-    const int KT = (p.K + KC - 1) / KC;
-    const int rows_valid = min(TM, p.M - m0), cols_valid = min(TN, p.N - n0);
+    const int KT = (p.K + KC - 1) / KC;                 // A slabs per tile
+    constexpr int APB = KCB / KC;                       // A slabs per B slab
+    const int tiles_m = (p.M + TM - 1) / TM, tiles_n = (p.N + TN - 1) / TN;
+    const long long ntiles = (long long)tiles_m * tiles_n * p.batch;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+        for (int s = 0; s < BSTAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], NCONS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
+    // PERSISTENT: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (m-tile fastest so that the CTAs running
+    // at the same time share the B / U12 columns in L2).  The producer runs ahead across tile boundaries, so the
+    // pipeline fill of the next tile is not exposed; the epilogue stores drain behind the next K loop.
     if (warp == NCONS) {
         // ---------------- producer warp: TMA bulk copies, one per contiguous column segment ----------------
-        for (int kt = 0; kt < KT; ++kt) {
-            const int s = kt % STAGES, k0 = kt * KC;
-            const int kv = min(KC, p.K - k0);
-            if (kt >= STAGES) mbar_wait(&empty[s], ((kt / STAGES) - 1) & 1);
-            if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)((kv * rows_valid + cols_valid * kv) * sizeof(cplx)));
-            __syncwarp();
-            cplx* a_s = sA + s * A_STAGE;
-            cplx* b_s = sB + s * B_STAGE;
-            if (lane < kv)
-                bulk_g2s(a_s + lane * LDSA, A + m0 + (long long)(k0 + lane) * p.lda,
-                         (uint32_t)(rows_valid * sizeof(cplx)), &full[s]);
-            for (int j = lane; j < cols_valid; j += 32)
-                bulk_g2s(b_s + j * LDSB, B + k0 + (long long)(n0 + j) * p.ldb, (uint32_t)(kv * sizeof(cplx)), &full[s]);
+        long long it = 0, ib = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int mt = (int)(tile % tiles_m), nt = (int)((tile / tiles_m) % tiles_n), bz = (int)(tile / ((long long)tiles_m * tiles_n));
+            const int m0 = mt * TM, n0 = nt * TN;
+            const cplx* A = p.A + (long long)bz * p.strideA;
+            const cplx* B = p.B + (long long)bz * p.strideB;
+            const int rows_valid = min(TM, p.M - m0), cols_valid = min(TN, p.N - n0);
+            if (p.beta) {
+                // warm L2 with the C tile of the NEXT tile of this CTA (and of the first one): the consumers initialise
+                // their accumulators from it at tile start, so the load must be an L2 hit by then
+                for (long long tn = (tile == blockIdx.x ? tile : tile + gridDim.x); tn < ntiles && tn <= tile + gridDim.x; tn += gridDim.x) {
+                    const int mt2 = (int)(tn % tiles_m), nt2 = (int)((tn / tiles_m) % tiles_n), bz2 = (int)(tn / ((long long)tiles_m * tiles_n));
+                    const cplx* C2 = p.C + (long long)bz2 * p.strideC + mt2 * TM + (long long)(nt2 * TN) * p.ldc;
+                    const int rv = min(TM, p.M - mt2 * TM), cvn = min(TN, p.N - nt2 * TN);
+                    for (int j = lane; j < cvn; j += 32)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(C2 + (long long)j * p.ldc),
+                                     "r"((uint32_t)(rv * sizeof(cplx))) : "memory");
+                }
+            }
+            for (int kt = 0; kt < KT; ++kt, ++it) {
+                if (kt % APB == 0) {
+                    const int sb = (int)(ib % BSTAGES), kb0 = kt * KC;
+                    const int kvb = min(KCB, p.K - kb0);
+                    if (ib >= BSTAGES) mbar_wait(&bempty[sb], (uint32_t)(((ib / BSTAGES) - 1) & 1));
+                    if (!(p.debug & 1)) {
+                        if (lane == 0) mbar_expect_tx(&bfull[sb], (uint32_t)(cols_valid * kvb * sizeof(cplx)));
+                        __syncwarp();
+                        cplx* b_s = sB + sb * B_STAGE;
+                        for (int j = lane; j < cols_valid; j += 32)
+                            bulk_g2s(b_s + j * LDSB, B + kb0 + (long long)(n0 + j) * p.ldb, (uint32_t)(kvb * sizeof(cplx)), &bfull[sb]);
+                    } else if (lane == 0) mbar_arrive(&bfull[sb]);
+                    ++ib;
+                }
+                const int s = (int)(it % STAGES), k0 = kt * KC;
+                const int kv = min(KC, p.K - k0);
+                if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
+                if (p.debug & 1) { if (lane == 0) mbar_arrive(&full[s]); continue; }
+                if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(kv * rows_valid * sizeof(cplx)));
+                __syncwarp();
+                if (lane < kv)
+                    bulk_g2s(sA + s * A_STAGE + lane * LDSA, A + m0 + (long long)(k0 + lane) * p.lda,
+                             (uint32_t)(rows_valid * sizeof(cplx)), &full[s]);
+            }
         }
         return;
     }
 
     // ---------------- consumer warps ----------------
-    const int wm = warp >> 2, wn = warp & 3;       // 2 x 4 warps
+    const int wm = warp >> 2, wn = warp & 3;       // NWM x 4 warps
     const int g = lane >> 2, t = lane & 3;         // fragment coordinates
-    double acc[8][4][2];
-    const int crow = m0 + wm * 64 + g;             // + 8*qa
-    const int ccol = n0 + wn * 16 + t;             // + 4*qb
-    if (p.beta) {
+    // B~ = [[br, bi], [-bi, br]]: this lane holds B~[kk = t][nn = g] -> component (t ^ g) & 1, negative iff (t odd, g even)
+    const int comp = (t ^ g) & 1;
+    const long long sflip = (((((t & 1) && !(g & 1)) ? 1 : 0) ^ (p.negate ? 1 : 0)) ? 1LL : 0LL) << 63;   // sign-bit flip
+    const int kh = t >> 1;                          // which of the two complex k of a k4 step
+    const int arow = wm * (8 * AB) + g;
+    const int bcol = wn * 16 + (g >> 1);
+    long long it = 0, ib = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int mt = (int)(tile % tiles_m), nt = (int)((tile / tiles_m) % tiles_n), bz = (int)(tile / ((long long)tiles_m * tiles_n));
+        const int m0 = mt * TM, n0 = nt * TN;
+        cplx* C = p.C + (long long)bz * p.strideC;
+        double acc[AB][4][2];
+        const int crow = m0 + wm * (8 * AB) + g;       // + 8*qa
+        const int ccol = n0 + wn * 16 + t;             // + 4*qb
+        if (p.beta && !(p.debug & 16)) {
+            // accumulators start from C (L2 hits: the producer prefetched this tile while the previous one was computed)
 #pragma unroll
-        for (int qa = 0; qa < 8; ++qa)
+            for (int qa = 0; qa < AB; ++qa)
+#pragma unroll
+                for (int qb = 0; qb < 4; ++qb) {
+                    int r = crow + 8 * qa, c = ccol + 4 * qb;
+                    cplx v = (r < p.M && c < p.N) ? __ldcg(&C[r + (long long)c * p.ldc]) : cmake(0.0, 0.0);
+                    acc[qa][qb][0] = v.x; acc[qa][qb][1] = v.y;
+                }
+        } else {
+#pragma unroll
+            for (int qa = 0; qa < AB; ++qa)
+#pragma unroll
+                for (int qb = 0; qb < 4; ++qb) { acc[qa][qb][0] = 0.0; acc[qa][qb][1] = 0.0; }
+        }
+        const double* b_s = nullptr;
+        int sb = 0;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+            if (kt % APB == 0) {
+                sb = (int)(ib % BSTAGES);
+                mbar_wait(&bfull[sb], (uint32_t)((ib / BSTAGES) & 1));
+                b_s = reinterpret_cast<const double*>(sB + sb * B_STAGE);
+                ++ib;
+            }
+            const int s = (int)(it % STAGES);
+            const int kv = min(KC, p.K - kt * KC);
+            const int kboff = (kt % APB) * KC;       // offset of this A slab inside the B slab
+            if (!(p.debug & 8)) mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+            const double* a_s = reinterpret_cast<const double*>(sA + s * A_STAGE);
+            if (p.debug & 2) {
+            } else if (kv == KC) {
+#pragma unroll
+                for (int ks = 0; ks < KC / 2; ++ks) {
+                    const int kc = 2 * ks + kh;
+                    double af[AB], bf[4];
+#pragma unroll
+                    for (int qa = 0; qa < AB; ++qa) af[qa] = a_s[2 * (kc * LDSA + arow + 8 * qa) + (t & 1)];
+#pragma unroll
+                    for (int qb = 0; qb < 4; ++qb)
+                        bf[qb] = __longlong_as_double(__double_as_longlong(b_s[2 * ((bcol + 4 * qb) * LDSB + kboff + kc) + comp]) ^ sflip);
+#pragma unroll
+                    for (int qa = 0; qa < AB; ++qa)
+#pragma unroll
+                        for (int qb = 0; qb < 4; ++qb) dmma884(acc[qa][qb][0], acc[qa][qb][1], af[qa], bf[qb]);
+                }
+            } else {
+                // K tail: complex k >= kv contribute exact zeros (both fragments are cleared in registers)
+                for (int ks = 0; 2 * ks < kv; ++ks) {
+                    const int kc = 2 * ks + kh;
+                    const bool ok = kc < kv;
+                    double af[AB], bf[4];
+#pragma unroll
+                    for (int qa = 0; qa < AB; ++qa) af[qa] = ok ? a_s[2 * (kc * LDSA + arow + 8 * qa) + (t & 1)] : 0.0;
+#pragma unroll
+                    for (int qb = 0; qb < 4; ++qb)
+                        bf[qb] = ok ? __longlong_as_double(__double_as_longlong(b_s[2 * ((bcol + 4 * qb) * LDSB + kboff + kc) + comp]) ^ sflip) : 0.0;
+#pragma unroll
+                    for (int qa = 0; qa < AB; ++qa)
+#pragma unroll
+                        for (int qb = 0; qb < 4; ++qb) dmma884(acc[qa][qb][0], acc[qa][qb][1], af[qa], bf[qb]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[s]);
+                if (kt % APB == APB - 1 || kt == KT - 1) mbar_arrive(&bempty[sb]);
+            }
+        }
+        if (p.debug & 4) { if (acc[0][0][0] == 1.2345e-300) C[0] = cmake(acc[1][1][0], acc[2][2][1]); continue; }
+#pragma unroll
+        for (int qa = 0; qa < AB; ++qa)
 #pragma unroll
             for (int qb = 0; qb < 4; ++qb) {
                 int r = crow + 8 * qa, c = ccol + 4 * qb;
-                cplx v = cmake(0.0, 0.0);
-                if (r < p.M && c < p.N) v = C[r + (long long)c * p.ldc];
-                acc[qa][qb][0] = v.x; acc[qa][qb][1] = v.y;
+                if (r < p.M && c < p.N && !((p.debug & 32) && acc[qa][qb][0] != 1.2345e-300)) C[r + (long long)c * p.ldc] = cmake(acc[qa][qb][0], acc[qa][qb][1]);
             }
-    } else {
-#pragma unroll
-        for (int qa = 0; qa < 8; ++qa)
-#pragma unroll
-            for (int qb = 0; qb < 4; ++qb) { acc[qa][qb][0] = 0.0; acc[qa][qb][1] = 0.0; }
     }
-    // B~ = [[br, bi], [-bi, br]]: this lane holds B~[kk = t][nn = g] -> component (t ^ g) & 1, negative iff (t odd, g even)
-    const int comp = (t ^ g) & 1;
-    const double sgn = ((((t & 1) && !(g & 1)) ? 1 : 0) ^ (p.negate ? 1 : 0)) ? -1.0 : 1.0;
-    const int kh = t >> 1;                          // which of the two complex k of a k4 step
-    const int arow = wm * 64 + g;
-    const int bcol = wn * 16 + (g >> 1);
-
-    for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % STAGES;
-        const int kv = min(KC, p.K - kt * KC);
-        mbar_wait(&full[s], (kt / STAGES) & 1);
-        const double* a_s = reinterpret_cast<const double*>(sA + s * A_STAGE);
-        const double* b_s = reinterpret_cast<const double*>(sB + s * B_STAGE);
-        if (kv == KC) {
-#pragma unroll
-            for (int ks = 0; ks < KC / 2; ++ks) {
-                const int kc = 2 * ks + kh;
-                double af[8], bf[4];
-#pragma unroll
-                for (int qa = 0; qa < 8; ++qa) af[qa] = a_s[2 * (kc * LDSA + arow + 8 * qa) + (t & 1)];
-#pragma unroll
-                for (int qb = 0; qb < 4; ++qb) bf[qb] = b_s[2 * ((bcol + 4 * qb) * LDSB + kc) + comp] * sgn;
-#pragma unroll
-                for (int qa = 0; qa < 8; ++qa)
-#pragma unroll
-                    for (int qb = 0; qb < 4; ++qb) dmma884(acc[qa][qb][0], acc[qa][qb][1], af[qa], bf[qb]);
-            }
-        } else {
-            // K tail: complex k >= kv contribute exact zeros (both fragments are cleared in registers)
-            for (int ks = 0; 2 * ks < kv; ++ks) {
-                const int kc = 2 * ks + kh;
-                const bool ok = kc < kv;
-                double af[8], bf[4];
-#pragma unroll
-                for (int qa = 0; qa < 8; ++qa) af[qa] = ok ? a_s[2 * (kc * LDSA + arow + 8 * qa) + (t & 1)] : 0.0;
-#pragma unroll
-                for (int qb = 0; qb < 4; ++qb) bf[qb] = ok ? b_s[2 * ((bcol + 4 * qb) * LDSB + kc) + comp] * sgn : 0.0;
-#pragma unroll
-                for (int qa = 0; qa < 8; ++qa)
-#pragma unroll
-                    for (int qb = 0; qb < 4; ++qb) dmma884(acc[qa][qb][0], acc[qa][qb][1], af[qa], bf[qb]);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-    }
-#pragma unroll
-    for (int qa = 0; qa < 8; ++qa)
-#pragma unroll
-        for (int qb = 0; qb < 4; ++qb) {
-            int r = crow + 8 * qa, c = ccol + 4 * qb;
-            if (r < p.M && c < p.N) C[r + (long long)c * p.ldc] = cmake(acc[qa][qb][0], acc[qa][qb][1]);
-        }
 }
 
 // Independent FP64-FMA implementation (16 x 16 tiles) -- test cross-check only.
@@ -201,20 +274,39 @@ __global__ void __launch_bounds__(256) zgemm_simple_kernel(ZgemmParams p) {
 
 }  // namespace
 
-cudaError_t zgemm_dmma_launch(const ZgemmParams& p, cudaStream_t stream) {
-    if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return cudaSuccess;
+template <int TM, int AB>
+static cudaError_t launch_cfg(const ZgemmParams& p, cudaStream_t stream) {
+    using CF = Cfg<TM, AB>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(zgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(zgemm_dmma_kernel<TM, AB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((p.M + TM - 1) / TM, (p.N + TN - 1) / TN, p.batch);
-    if (p.K <= 0) {   // nothing to accumulate: C = beta*C
-        if (p.beta) return cudaSuccess;
-    }
-    zgemm_dmma_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(p);
+    const long long ntiles = (long long)((p.M + TM - 1) / TM) * ((p.N + TN - 1) / TN) * p.batch;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = MAUS_SM_COUNT_B200; }
+    const long long slots = (long long)sms * CF::CTAS_PER_SM;
+    const unsigned grid = (unsigned)(ntiles < slots ? ntiles : slots);     // persistent: CTAS_PER_SM CTAs per SM
+    zgemm_dmma_kernel<TM, AB><<<grid, CF::NTHREADS, CF::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
+}
+
+static int g_zgemm_cfg = -1;
+void zgemm_set_config(int cfg) { g_zgemm_cfg = cfg; }
+
+cudaError_t zgemm_dmma_launch(const ZgemmParams& p, cudaStream_t stream) {
+    if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return cudaSuccess;
+    if (p.K <= 0 && p.beta) return cudaSuccess;          // nothing to accumulate: C = C
+    if (g_zgemm_cfg < 0) {
+        const char* e = getenv("MAUS_GEMM_CFG");
+        g_zgemm_cfg = e ? atoi(e) : 0;
+    }
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MAUS_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } const_cast<ZgemmParams&>(p).debug = dbg; }
+    if ((const void*)p.C == (const void*)p.B) return launch_cfg<128, 8>(p, stream);   // in-place (U12 = L11^-1 A12): one row tile must own all rows
+    if (g_zgemm_cfg == 1) return launch_cfg<128, 4>(p, stream);
+    if (g_zgemm_cfg == 3) return launch_cfg<64, 8>(p, stream);   // 64 x 64 tiles, 2 CTAs / SM
+    return launch_cfg<128, 8>(p, stream);                    // default: 128 x 64 tiles, 8 consumer warps, 1 CTA / SM
 }
 
 cudaError_t zgemm_simple_launch(const ZgemmParams& p, cudaStream_t stream) {

@@ -9,9 +9,10 @@ struct ZgemmParams {
     int M, N, K, batch;
     int beta;      // 0: C = s*A*B        1: C = C + s*A*B
     int negate;    // s = -1 when set, else +1
+    int debug;     // experiments only: bit0 = producer skips the copies, bit1 = consumers skip the MMAs
 };
 
-// Tensor-pipe kernel (any M, N, K >= 1).  In-place use (C aliasing B) is safe when M <= 128 (one row tile).
+// Tensor-pipe kernel (any M, N, K >= 1).  In-place use (C == B) is supported for M <= 128: it is routed to the 128-row tile configuration so one CTA owns all rows of its columns.
 cudaError_t zgemm_dmma_launch(const ZgemmParams& p, cudaStream_t stream);
 // Plain FP64-FMA kernel, independent code path used by the tests to cross-check the tensor-pipe kernel.
 cudaError_t zgemm_simple_launch(const ZgemmParams& p, cudaStream_t stream);

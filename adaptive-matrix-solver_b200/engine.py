@@ -98,6 +98,17 @@ class MausEngine:
         return dict(lu_gemm_ms=a.value, lu_gemm_launches=b.value, lu_gemm_flops=c.value, matvec_ms=d.value,
                     matvec_launches=e.value, matvec_bytes=f.value)
 
+    PROF_KINDS = ("lu_gemm", "matvec", "panel", "trtri", "backsolve", "build", "permute", "matvec_gemm")
+
+    def profile_breakdown(self):
+        """{kind: dict(ms, launches, work)} accumulated since profile_reset(True)"""
+        out = {}
+        for k, name in enumerate(self.PROF_KINDS):
+            ms, ln, wk = C.c_double(), C.c_int64(), C.c_double()
+            self._check(self._lib.maus_profile_read_kind(self._h, k, C.byref(ms), C.byref(ln), C.byref(wk)))
+            out[name] = dict(ms=ms.value, launches=ln.value, work=wk.value)
+        return out
+
     # -- problem ----------------------------------------------------------------------------------------------
     def set_matrix(self, A, slot=_abi.SLOT_CURRENT):
         """A: numpy 2-D array (any dtype, coerced like AMS:343) or scipy.sparse matrix (kept sparse, AMS:342)."""

@@ -164,6 +164,7 @@ def run_b200(args):
     dev_ms = e0.elapsed_time(e1)
     launches = eng.launches - l0
     prof = eng.profile_read()
+    breakdown = eng.profile_breakdown()
     eng.profile_reset(False)
     clocks = sampler.stop() if rank == 0 else None
     # device time never exceeds host wall here (every step ends with a stream sync); report the max over ranks
@@ -215,6 +216,7 @@ def run_b200(args):
                         "d2h_bytes_per_step": vec_bytes + 48 * C_, "steps": e2e_steps,
                         "api": "step_population(candidates, M, b, strat_params, problem_knowledge, engine)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "step_breakdown_ms": {k: round(v["ms"] / args.steps, 2) for k, v in breakdown.items() if v["launches"]},
                 "wall_s_timed": round(wall, 3), "min_residual": float(np.min(out["resid"]))}
         print(json.dumps(line), flush=True)
     if world > 1:

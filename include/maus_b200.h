@@ -154,6 +154,16 @@ int64_t maus_launch_count(maus_ctx* ctx);
 int maus_profile_reset(maus_ctx* ctx, int enable);
 int maus_profile_read(maus_ctx* ctx, double* lu_gemm_ms, int64_t* lu_gemm_launches, double* lu_gemm_flops,
                       double* matvec_ms, int64_t* matvec_launches, double* matvec_bytes);
+/* per-kernel-family accumulators (device ms, launches, flops or bytes) for the step breakdown */
+#define MAUS_PROF_LU_GEMM     0   /* zgemm_dmma_kernel inside the LU (flops) */
+#define MAUS_PROF_MATVEC      1   /* gemv_rowmajor_kernel / csr_spmm_kernel (bytes) */
+#define MAUS_PROF_PANEL       2   /* lu_panel_kernel (flops) */
+#define MAUS_PROF_TRTRI       3
+#define MAUS_PROF_BACKSOLVE   4   /* lu_backsolve_kernel (bytes) */
+#define MAUS_PROF_BUILD       5   /* lu_build_aug_kernel (bytes) */
+#define MAUS_PROF_PERMUTE     6
+#define MAUS_PROF_MATVEC_GEMM 7   /* zgemm_dmma_kernel as batched A*V (flops) */
+int maus_profile_read_kind(maus_ctx* ctx, int kind, double* ms, int64_t* launches, double* work);
 /* the context's CUDA stream as a void* (cudaStream_t) so a host layer can order its own work after it */
 void* maus_stream(maus_ctx* ctx);
 

@@ -20,9 +20,16 @@ eng = pkg.MausEngine(0)
 eng.set_matrix(A)
 eng.upload_vectors(V)
 alpha = np.full(C_, 0.01); psi = np.full(C_, 1e-20)
+eng.step(_abi.EIGENVALUE, alpha, psi, V=None, rng_key=np.arange(C_, dtype=np.uint64))   # warm-up (allocations)
+eng.profile_reset(True)
 for s in range(steps):
     t0 = time.perf_counter()
     out = eng.step(_abi.EIGENVALUE, alpha, psi, V=None, rng_key=np.arange(C_, dtype=np.uint64) + np.uint64(1000 * s))
     print(f"step {s}: {1e3 * (time.perf_counter() - t0):.1f} ms, launches so far {eng.launches}, min resid {out['resid'].min():.3e}",
           flush=True)
+bd = eng.profile_breakdown()
+for k, v in bd.items():
+    if v['launches']:
+        extra = f"  {v['work'] / v['ms'] / 1e9:.2f} TFLOP/s" if k in ('lu_gemm', 'matvec_gemm', 'panel') and v['ms'] > 0 else ''
+        print(f"  {k:12s} {v['ms'] / steps:9.3f} ms/step  launches/step {v['launches'] // steps}{extra}")
 eng.close()
