@@ -15,6 +15,7 @@
 //   lu_trtri        inverse of the unit-lower 128 x 128 diagonal block, so that the triangular solve for U12 and the
 //                   trailing update are both plain GEMMs on the FP64 tensor pipe (zgemm.cu).
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "lu.cuh"
 #include "../../include/maus_b200.h"
 
@@ -434,7 +435,16 @@ cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batc
                      cudaStream_t stream) {
     const int m = n - k0;
     if (m > LU_MAX_N) return cudaErrorInvalidValue;
-    int R = (m > PANEL_MAXC * PANEL_NT) ? 2 : 1;
+    // Rows per thread R: fewer, fatter CTAs cost less SM-time per panel (the column loop is latency-bound), more CTAs
+    // shorten a single panel.  Batches of >= 12 candidates are SM-time bound -> R = 2 (measured: -23 % panel time at 64
+    // candidates); small batches are latency bound -> R = 1.  R = 4 spills and was not faster.
+    static int force_r = -1;
+    if (force_r < 0) { const char* e = getenv("MAUS_PANEL_R"); force_r = e ? atoi(e) : 0; }
+    int R = 1;
+    if (batch >= 12) R = 2;
+    if (force_r == 1 || force_r == 2) R = force_r;
+    while (R < 2 && m > PANEL_MAXC * PANEL_NT * R) R <<= 1;         // all rows must be owned by one cluster
+    while (R > 1 && m <= PANEL_NT * (R / 2)) R >>= 1;                // do not leave most threads without rows
     int need = (m + R * PANEL_NT - 1) / (R * PANEL_NT);
     int nc = 1;
     while (nc < need) nc <<= 1;
