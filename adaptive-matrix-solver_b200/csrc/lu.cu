@@ -57,7 +57,6 @@ __global__ void __launch_bounds__(256) lu_build_aug_kernel(cplx* W, long long st
 // ------------------------------------------------------------------------------------------------------------
 // Panel factorisation
 // ------------------------------------------------------------------------------------------------------------
-constexpr int PANEL_NT = 512;
 constexpr int PANEL_MAXC = 8;
 
 template <int IB>
@@ -69,8 +68,8 @@ struct PanelSlot {
     cplx data[IB];     // that row's inner-block entries
 };
 
-template <int R, int IB>
-__global__ void __launch_bounds__(PANEL_NT, 1)
+template <int R, int IB, int PANEL_NT>
+__global__ void __launch_bounds__(PANEL_NT, (PANEL_NT <= 256) ? 2 : 1)
 lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pairs, int* info) {
     cg::cluster_group cluster = cg::this_cluster();
     const int NC = (int)cluster.num_blocks();
@@ -318,29 +317,46 @@ __global__ void __launch_bounds__(256) lu_permute_rows_kernel(cplx* W, long long
 // ------------------------------------------------------------------------------------------------------------
 // Inverse of the unit-lower-triangular diagonal block
 // ------------------------------------------------------------------------------------------------------------
-// thread c owns column c of X = L11^-1; X is kept packed (row p holds columns 0..p) in shared memory.
-__global__ void __launch_bounds__(LU_NB) lu_trtri_kernel(const cplx* __restrict__ W, long long strideW, int n, int k0,
+// thread c owns column c of X = L11^-1; X is kept packed (row p holds columns 0..p) in shared memory.  Rows of L11 are
+// streamed through a ring of TRTRI_PF row buffers with cp.async so the global-load latency of row r + TRTRI_PF - 1
+// hides behind the arithmetic of rows r .. r + TRTRI_PF - 2 (the one-row-ahead version was latency-bound: 353 us).
+constexpr int TRTRI_PF = 8;
+constexpr int TRTRI_SPLIT = 4;     // lanes sharing one column's dot product (critical path / 4)
+__global__ void __launch_bounds__(LU_NB * TRTRI_SPLIT) lu_trtri_kernel(const cplx* __restrict__ W, long long strideW, int n, int k0,
                                                          int jb, cplx* __restrict__ Linv) {
     extern __shared__ __align__(16) unsigned char trtri_smem[];
     cplx* X = reinterpret_cast<cplx*>(trtri_smem);                 // jb*(jb+1)/2
-    cplx* rowbuf = X + (LU_NB * (LU_NB + 1)) / 2;                  // 2 x LU_NB (double buffered row of L)
-    const int b = blockIdx.x, c = threadIdx.x;
+    cplx* rowbuf = X + (LU_NB * (LU_NB + 1)) / 2;                  // TRTRI_PF x LU_NB ring of rows of L
+    const int b = blockIdx.x, c = threadIdx.x / TRTRI_SPLIT, sp = threadIdx.x % TRTRI_SPLIT;
     const cplx* L = W + (long long)b * strideW + (long long)k0 * n + k0;   // L[r + p*n]
-    if (c < jb) X[(c * (c + 1)) / 2 + c] = cmake(1.0, 0.0);
-    if (jb > 1 && c < 1) rowbuf[LU_NB + c] = L[1 + (long long)c * n];     // row 1 lives in buffer (1 & 1)
-    __syncthreads();
-    for (int r = 1; r < jb; ++r) {
-        const cplx* lr = rowbuf + (r & 1) * LU_NB;
-        if (r + 1 < jb && c < r + 1) rowbuf[((r + 1) & 1) * LU_NB + c] = L[(r + 1) + (long long)c * n];   // prefetch next row
-        if (c < r) {
-            cplx acc = cmake(0.0, 0.0);
-            for (int p = c; p < r; ++p) cfms(acc, lr[p], X[(p * (p + 1)) / 2 + c]);
-            X[(r * (r + 1)) / 2 + c] = acc;
+    if (c < jb && sp == 0) X[(c * (c + 1)) / 2 + c] = cmake(1.0, 0.0);
+    auto fetch_row = [&](int r) {
+        if (r < jb && c < r && sp == 0) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&rowbuf[(r % TRTRI_PF) * LU_NB + c]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(L + r + (long long)c * n) : "memory");
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int r = 1; r < TRTRI_PF; ++r) fetch_row(r);
+    for (int r = 1; r < jb; ++r) {
+        fetch_row(r + TRTRI_PF - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(TRTRI_PF - 1) : "memory");     // row r has landed (for this thread)
+        __syncthreads();                                                             // ... and for every thread
+        const cplx* lr = rowbuf + (r % TRTRI_PF) * LU_NB;
+        {
+            cplx acc = cmake(0.0, 0.0);
+            if (c < r)
+                for (int p = c + sp; p < r; p += TRTRI_SPLIT) cfms(acc, lr[p], X[(p * (p + 1)) / 2 + c]);
+#pragma unroll
+            for (int o = TRTRI_SPLIT / 2; o > 0; o >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            }
+            if (c < r && sp == 0) X[(r * (r + 1)) / 2 + c] = acc;
+        }
+        __syncthreads();       // X row r complete; ring slot r % PF may be refilled by the next fetch
     }
     cplx* out = Linv + (long long)b * LU_NB * LU_NB;
-    for (int r = 0; r < jb; ++r)
+    for (int r = sp; r < jb; r += TRTRI_SPLIT)
         if (c < jb) out[r + c * LU_NB] = (c <= r) ? X[(r * (r + 1)) / 2 + c] : cmake(0.0, 0.0);
 }
 
@@ -416,7 +432,7 @@ cudaError_t lu_build_aug(cplx* W, long long strideW, int n, int batch, const cpl
     return cudaGetLastError();
 }
 
-template <int R, int IB>
+template <int R, int IB, int PANEL_NT>
 static cudaError_t launch_panel(cplx* W, long long strideW, int n, int k0, int jb, int batch, LuPairs* pairs, int* info,
                                 int nc, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
@@ -428,7 +444,7 @@ static cudaError_t launch_panel(cplx* W, long long strideW, int n, int k0, int j
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, lu_panel_kernel<R, IB>, W, strideW, n, k0, jb, pairs, info);
+    return cudaLaunchKernelEx(&cfg, lu_panel_kernel<R, IB, PANEL_NT>, W, strideW, n, k0, jb, pairs, info);
 }
 
 cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batch, LuPairs* pairs, int* info,
@@ -440,16 +456,21 @@ cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batc
     // candidates); small batches are latency bound -> R = 1.  R = 4 spills and was not faster.
     static int force_r = -1;
     if (force_r < 0) { const char* e = getenv("MAUS_PANEL_R"); force_r = e ? atoi(e) : 0; }
-    int R = 1;
-    if (batch >= 12) R = 2;
-    if (force_r == 1 || force_r == 2) R = force_r;
-    while (R < 2 && m > PANEL_MAXC * PANEL_NT * R) R <<= 1;         // all rows must be owned by one cluster
-    while (R > 1 && m <= PANEL_NT * (R / 2)) R >>= 1;                // do not leave most threads without rows
-    int need = (m + R * PANEL_NT - 1) / (R * PANEL_NT);
+    // configurations (rows per cluster = NC * NT * R, NC <= 8):
+    //   A: NT 512, R 1, IB 16 -> <= 4096 rows, lowest latency (small batches)
+    //   B: NT 256, R 2, IB 8  -> <= 4096 rows, two CTAs of different clusters share an SM so one cluster's barrier
+    //                            latency hides behind the other's arithmetic (large batches are SM-time bound)
+    //   C: NT 512, R 2, IB 8  -> <= 8192 rows
+    int mode = (batch >= 12) ? 1 : 0;
+    if (force_r == 1) mode = 0; else if (force_r == 2) mode = 2; else if (force_r == 3) mode = 1;
+    if (m > PANEL_MAXC * 512) mode = 2;
+    const int rows_per_cta = (mode == 0) ? 512 : (mode == 1 ? 512 : 1024);
+    int need = (m + rows_per_cta - 1) / rows_per_cta;
     int nc = 1;
     while (nc < need) nc <<= 1;
-    if (R == 1) return launch_panel<1, 16>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
-    return launch_panel<2, 8>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+    if (mode == 0) return launch_panel<1, 16, 512>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+    if (mode == 1) return launch_panel<2, 8, 256>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+    return launch_panel<2, 8, 512>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
 }
 
 cudaError_t lu_permute_rows(cplx* W, long long strideW, int n, int k0, int batch, const LuPairs* pairs,
@@ -461,14 +482,14 @@ cudaError_t lu_permute_rows(cplx* W, long long strideW, int n, int k0, int batch
 }
 
 cudaError_t lu_trtri(const cplx* W, long long strideW, int n, int k0, int jb, int batch, cplx* Linv, cudaStream_t stream) {
-    const size_t smem = ((size_t)(LU_NB * (LU_NB + 1)) / 2 + 2 * LU_NB) * sizeof(cplx);
+    const size_t smem = ((size_t)(LU_NB * (LU_NB + 1)) / 2 + TRTRI_PF * LU_NB) * sizeof(cplx);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(lu_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    lu_trtri_kernel<<<batch, LU_NB, smem, stream>>>(W, strideW, n, k0, jb, Linv);
+    lu_trtri_kernel<<<batch, LU_NB * TRTRI_SPLIT, smem, stream>>>(W, strideW, n, k0, jb, Linv);
     return cudaGetLastError();
 }
 
