@@ -290,7 +290,7 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
 // Row permutation of all columns >= k0
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PERM_COLS = 8;
-__global__ void __launch_bounds__(256) lu_permute_rows_kernel(cplx* W, long long strideW, int n, int k0,
+__global__ void __launch_bounds__(256) lu_permute_rows_kernel(cplx* W, long long strideW, int n, int k0, int colstart,
                                                               const LuPairs* __restrict__ pairs) {
     __shared__ cplx tmp[LU_MAX_PAIRS * PERM_COLS];
     __shared__ int sdst[LU_MAX_PAIRS], ssrc[LU_MAX_PAIRS];
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) lu_permute_rows_kernel(cplx* W, long long
     if (cnt == 0) return;
     for (int q = threadIdx.x; q < cnt; q += blockDim.x) { sdst[q] = pairs[b].dst[q]; ssrc[q] = pairs[b].src[q]; }
     __syncthreads();
-    const int col0 = k0 + blockIdx.x * PERM_COLS;
+    const int col0 = colstart + blockIdx.x * PERM_COLS;
     const int ncol = min(PERM_COLS, n + 1 - col0);
     cplx* Wb = W + (long long)b * strideW + k0;
     const int total = cnt * ncol;
@@ -473,11 +473,11 @@ cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batc
     return launch_panel<2, 8, 512>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
 }
 
-cudaError_t lu_permute_rows(cplx* W, long long strideW, int n, int k0, int batch, const LuPairs* pairs,
+cudaError_t lu_permute_rows(cplx* W, long long strideW, int n, int k0, int colstart, int batch, const LuPairs* pairs,
                             cudaStream_t stream) {
-    const int ncols = n + 1 - k0;
+    const int ncols = n + 1 - colstart;
     dim3 grid((ncols + PERM_COLS - 1) / PERM_COLS, batch, 1);
-    lu_permute_rows_kernel<<<grid, 256, 0, stream>>>(W, strideW, n, k0, pairs);
+    lu_permute_rows_kernel<<<grid, 256, 0, stream>>>(W, strideW, n, k0, colstart, pairs);
     return cudaGetLastError();
 }
 

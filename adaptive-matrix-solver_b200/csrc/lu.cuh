@@ -23,8 +23,9 @@ cudaError_t lu_build_aug(cplx* W, long long strideW, int n, int batch, const cpl
 // one panel step k0: factor W[k0:n, k0:k0+jb] with implicit partial pivoting, emit the row permutation.
 cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batch, LuPairs* pairs, int* info,
                      cudaStream_t stream);
-// apply the panel's row permutation to columns [k0, n] (panel, trailing matrix and rhs column)
-cudaError_t lu_permute_rows(cplx* W, long long strideW, int n, int k0, int batch, const LuPairs* pairs,
+// apply the panel's row permutation (rows relative to k0) to columns [colstart, n]: the panel, the trailing matrix, the
+// rhs column and -- for the second panel of a pair -- the previous panel's L21 whose update is still pending
+cudaError_t lu_permute_rows(cplx* W, long long strideW, int n, int k0, int colstart, int batch, const LuPairs* pairs,
                             cudaStream_t stream);
 // Linv_b = inverse of the unit-lower-triangular L11 block (jb x jb, ld = LU_NB)
 cudaError_t lu_trtri(const cplx* W, long long strideW, int n, int k0, int jb, int batch, cplx* Linv,

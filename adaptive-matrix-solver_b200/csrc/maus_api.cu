@@ -453,41 +453,64 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
         prof_end(ctx, hb);
         MAUS_CUDA(ctx, cudaMemsetAsync(ctx->info, 0, (size_t)nb * sizeof(int), st));
         ctx->launches += 1;
-        for (int k0 = 0; k0 < n; k0 += LU_NB) {
-            const int jb = std::min(LU_NB, n - k0);
-            int hp = prof_begin(ctx, MAUS_PROF_PANEL, 8.0 * (n - k0) * (double)jb * jb * 0.5 * nb);
-            MAUS_CUDA(ctx, lu_panel(ctx->W, strideW, n, k0, jb, nb, ctx->pairs, ctx->info, st));
-            prof_end(ctx, hp);
-            hp = prof_begin(ctx, MAUS_PROF_PERMUTE, 0.0);
-            MAUS_CUDA(ctx, lu_permute_rows(ctx->W, strideW, n, k0, nb, ctx->pairs, st));
-            prof_end(ctx, hp);
-            ctx->launches += 2;
-            const int ncols = n + 1 - (k0 + jb);       // trailing columns incl. the rhs column
-            if (ncols <= 0) continue;
-            hp = prof_begin(ctx, MAUS_PROF_TRTRI, 0.0);
-            MAUS_CUDA(ctx, lu_trtri(ctx->W, strideW, n, k0, jb, nb, ctx->Linv, st));
-            prof_end(ctx, hp);
+        // Panels are processed in PAIRS: after panel 1 only the columns of panel 2 and the rows of block 2 are updated
+        // (two narrow GEMMs); the rest of the trailing matrix receives both rank-128 updates in ONE GEMM with K = 256,
+        // which halves the C-tile traffic / per-tile overhead of the dominant kernel.
+        auto W_at = [&](long long r, long long c) { return ctx->W + c * n + r; };
+        auto gemm = [&](const cplx* A, long long lda, long long sA, const cplx* B, cplx* C, int M, int N, int K, int beta,
+                        int negate) -> cudaError_t {
             ZgemmParams p = {};
-            cplx* A12 = ctx->W + (long long)(k0 + jb) * n + k0;
-            p.A = ctx->Linv; p.lda = LU_NB; p.strideA = (long long)LU_NB * LU_NB;
-            p.B = A12; p.ldb = n; p.strideB = strideW;
-            p.C = A12; p.ldc = n; p.strideC = strideW;
-            p.M = jb; p.N = ncols; p.K = jb; p.batch = nb; p.beta = 0; p.negate = 0;
-            int h = prof_begin(ctx, MAUS_PROF_LU_GEMM, 8.0 * jb * (double)ncols * jb * nb);
-            MAUS_CUDA(ctx, zgemm_dmma_launch(p, st));            // U12 = L11^-1 A12 (in place, one row tile)
+            p.A = A; p.lda = lda; p.strideA = sA;
+            p.B = B; p.ldb = n; p.strideB = strideW;
+            p.C = C; p.ldc = n; p.strideC = strideW;
+            p.M = M; p.N = N; p.K = K; p.batch = nb; p.beta = beta; p.negate = negate;
+            int h = prof_begin(ctx, MAUS_PROF_LU_GEMM, 8.0 * M * (double)N * K * nb);
+            cudaError_t e = zgemm_dmma_launch(p, st);
             prof_end(ctx, h);
+            ctx->launches += 1;
+            return e;
+        };
+        auto factor_panel = [&](int k0, int jb, int colstart) -> cudaError_t {
+            int hp = prof_begin(ctx, MAUS_PROF_PANEL, 8.0 * (n - k0) * (double)jb * jb * 0.5 * nb);
+            cudaError_t e = lu_panel(ctx->W, strideW, n, k0, jb, nb, ctx->pairs, ctx->info, st);
+            prof_end(ctx, hp);
+            if (e != cudaSuccess) return e;
+            hp = prof_begin(ctx, MAUS_PROF_PERMUTE, 0.0);
+            e = lu_permute_rows(ctx->W, strideW, n, k0, colstart, nb, ctx->pairs, st);
+            prof_end(ctx, hp);
             ctx->launches += 2;
-            const int m2 = n - k0 - jb;
-            if (m2 > 0) {
-                p.A = ctx->W + (long long)k0 * n + (k0 + jb); p.lda = n; p.strideA = strideW;        // L21
-                p.B = A12;                                                                           // U12
-                p.C = ctx->W + (long long)(k0 + jb) * n + (k0 + jb);                                 // A22
-                p.M = m2; p.N = ncols; p.K = jb; p.beta = 1; p.negate = 1;
-                h = prof_begin(ctx, MAUS_PROF_LU_GEMM, 8.0 * m2 * (double)ncols * jb * nb);
-                MAUS_CUDA(ctx, zgemm_dmma_launch(p, st));
-                prof_end(ctx, h);
-                ctx->launches += 1;
-            }
+            return e;
+        };
+        auto solve_u12 = [&](int k0, int jb, int ncols) -> cudaError_t {     // U12 = L11^-1 A12, in place
+            int hp = prof_begin(ctx, MAUS_PROF_TRTRI, 0.0);
+            cudaError_t e = lu_trtri(ctx->W, strideW, n, k0, jb, nb, ctx->Linv, st);
+            prof_end(ctx, hp);
+            ctx->launches += 1;
+            if (e != cudaSuccess) return e;
+            cplx* A12 = W_at(k0, k0 + jb);
+            return gemm(ctx->Linv, LU_NB, (long long)LU_NB * LU_NB, A12, A12, jb, ncols, jb, 0, 0);
+        };
+        for (int k0 = 0; k0 < n; k0 += 2 * LU_NB) {
+            const int jb1 = std::min(LU_NB, n - k0);
+            MAUS_CUDA(ctx, factor_panel(k0, jb1, k0));
+            const int k1 = k0 + jb1;
+            const int nc1 = n + 1 - k1;                    // columns right of panel 1, incl. the rhs column
+            MAUS_CUDA(ctx, solve_u12(k0, jb1, nc1));
+            const int m1 = n - k1;                         // rows below block 1
+            if (m1 <= 0) continue;
+            const int jb2 = std::min(LU_NB, n - k1);
+            // (a) columns of panel 2, all rows below block 1
+            MAUS_CUDA(ctx, gemm(W_at(k1, k0), n, strideW, W_at(k0, k1), W_at(k1, k1), m1, jb2, jb1, 1, 1));
+            const int k2 = k1 + jb2;
+            const int nc2 = n + 1 - k2;
+            // panel 2; its permutation also reorders L21 of panel 1 (columns k0..k1), whose update is still pending
+            MAUS_CUDA(ctx, factor_panel(k1, jb2, k0));
+            // (b) rows of block 2 (AFTER the pivoting of panel 2 decided which rows those are), columns right of panel 2
+            MAUS_CUDA(ctx, gemm(W_at(k1, k0), n, strideW, W_at(k0, k2), W_at(k1, k2), jb2, nc2, jb1, 1, 1));
+            MAUS_CUDA(ctx, solve_u12(k1, jb2, nc2));
+            const int m2 = n - k2;
+            if (m2 > 0)
+                MAUS_CUDA(ctx, gemm(W_at(k2, k0), n, strideW, W_at(k0, k2), W_at(k2, k2), m2, nc2, jb1 + jb2, 1, 1));
         }
         hb = prof_begin(ctx, MAUS_PROF_BACKSOLVE, 8.0 * n * (double)n * nb);
         MAUS_CUDA(ctx, lu_backsolve(ctx->W, strideW, n, nb, ctx->info, X + c0 * n, status + c0, st));
