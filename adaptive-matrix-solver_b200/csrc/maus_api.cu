@@ -1,5 +1,6 @@
 // maus_api.cu -- C ABI of libmaus_b200.so (see include/maus_b200.h for the contract and reference citations).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <algorithm>
@@ -453,9 +454,10 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
         prof_end(ctx, hb);
         MAUS_CUDA(ctx, cudaMemsetAsync(ctx->info, 0, (size_t)nb * sizeof(int), st));
         ctx->launches += 1;
-        // Panels are processed in PAIRS: after panel 1 only the columns of panel 2 and the rows of block 2 are updated
-        // (two narrow GEMMs); the rest of the trailing matrix receives both rank-128 updates in ONE GEMM with K = 256,
-        // which halves the C-tile traffic / per-tile overhead of the dominant kernel.
+        // Blocked two-level right-looking LU: LU_GROUP panels of width 128 form an outer block.  Inside the block every
+        // panel only updates (a) the block's remaining columns and (b) its own row block; the trailing matrix right of /
+        // below the outer block receives all LU_GROUP rank-128 updates in ONE GEMM with K = 128 * LU_GROUP, which divides
+        // the C-tile traffic and per-tile overhead of the dominant kernel by LU_GROUP.
         auto W_at = [&](long long r, long long c) { return ctx->W + c * n + r; };
         auto gemm = [&](const cplx* A, long long lda, long long sA, const cplx* B, cplx* C, int M, int N, int K, int beta,
                         int negate) -> cudaError_t {
@@ -490,27 +492,31 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
             cplx* A12 = W_at(k0, k0 + jb);
             return gemm(ctx->Linv, LU_NB, (long long)LU_NB * LU_NB, A12, A12, jb, ncols, jb, 0, 0);
         };
-        for (int k0 = 0; k0 < n; k0 += 2 * LU_NB) {
-            const int jb1 = std::min(LU_NB, n - k0);
-            MAUS_CUDA(ctx, factor_panel(k0, jb1, k0));
-            const int k1 = k0 + jb1;
-            const int nc1 = n + 1 - k1;                    // columns right of panel 1, incl. the rhs column
-            MAUS_CUDA(ctx, solve_u12(k0, jb1, nc1));
-            const int m1 = n - k1;                         // rows below block 1
-            if (m1 <= 0) continue;
-            const int jb2 = std::min(LU_NB, n - k1);
-            // (a) columns of panel 2, all rows below block 1
-            MAUS_CUDA(ctx, gemm(W_at(k1, k0), n, strideW, W_at(k0, k1), W_at(k1, k1), m1, jb2, jb1, 1, 1));
-            const int k2 = k1 + jb2;
-            const int nc2 = n + 1 - k2;
-            // panel 2; its permutation also reorders L21 of panel 1 (columns k0..k1), whose update is still pending
-            MAUS_CUDA(ctx, factor_panel(k1, jb2, k0));
-            // (b) rows of block 2 (AFTER the pivoting of panel 2 decided which rows those are), columns right of panel 2
-            MAUS_CUDA(ctx, gemm(W_at(k1, k0), n, strideW, W_at(k0, k2), W_at(k1, k2), jb2, nc2, jb1, 1, 1));
-            MAUS_CUDA(ctx, solve_u12(k1, jb2, nc2));
-            const int m2 = n - k2;
-            if (m2 > 0)
-                MAUS_CUDA(ctx, gemm(W_at(k2, k0), n, strideW, W_at(k0, k2), W_at(k2, k2), m2, nc2, jb1 + jb2, 1, 1));
+        static int lu_group = 0;
+        if (!lu_group) { const char* e = getenv("MAUS_LU_GROUP"); lu_group = e ? std::max(1, atoi(e)) : 4; }
+        for (int k0 = 0; k0 < n; k0 += lu_group * LU_NB) {
+            const int kend = std::min(n, k0 + lu_group * LU_NB);       // end of the outer block
+            const int nc_out = n + 1 - kend;                           // columns right of the outer block (incl. rhs)
+            for (int kp = k0; kp < kend; kp += LU_NB) {
+                const int jb = std::min(LU_NB, kend - kp);
+                // the panel's columns are up to date (updates (a) of the previous panels of this block);
+                // its permutation also reorders the L columns k0..kp of the block, whose trailing update is pending
+                MAUS_CUDA(ctx, factor_panel(kp, jb, k0));
+                const int kq = kp + jb;
+                // (b) this row block, columns right of the outer block: pending updates of the block's earlier panels
+                if (kp > k0 && nc_out > 0)
+                    MAUS_CUDA(ctx, gemm(W_at(kp, k0), n, strideW, W_at(k0, kend), W_at(kp, kend), jb, nc_out, kp - k0, 1, 1));
+                // U12 of this row block for every column right of the panel
+                MAUS_CUDA(ctx, solve_u12(kp, jb, n + 1 - kq));
+                // (a) remaining columns of the outer block, all rows below this row block
+                const int m_below = n - kq, n_in = kend - kq;
+                if (m_below > 0 && n_in > 0)
+                    MAUS_CUDA(ctx, gemm(W_at(kq, kp), n, strideW, W_at(kp, kq), W_at(kq, kq), m_below, n_in, jb, 1, 1));
+            }
+            // bulk update of everything right of and below the outer block
+            const int m_out = n - kend;
+            if (m_out > 0 && nc_out > 0)
+                MAUS_CUDA(ctx, gemm(W_at(kend, k0), n, strideW, W_at(k0, kend), W_at(kend, kend), m_out, nc_out, kend - k0, 1, 1));
         }
         hb = prof_begin(ctx, MAUS_PROF_BACKSOLVE, 8.0 * n * (double)n * nb);
         MAUS_CUDA(ctx, lu_backsolve(ctx->W, strideW, n, nb, ctx->info, X + c0 * n, status + c0, st));
