@@ -151,15 +151,15 @@ __global__ void __launch_bounds__(RED_NT) nan_scan_kernel(const cplx* __restrict
 // ---- HBM-bound batched matvec: Y[c] = A_rm * V[c] -------------------------------------------------------------
 // One warp per matrix row (coalesced 512 B row segments, warp-shuffle dot-product reduction); CB candidate vectors
 // are staged through shared memory in chunks so the matrix is streamed from HBM exactly once per CB candidates.
-constexpr int GV_NT = 256, GV_ROWS = 16, GV_JC = 512;
-template <int CB>
+constexpr int GV_NT = 256, GV_JC = 512;
+template <int CB, int RPW>      // CB candidates per pass, RPW rows per warp (the staged vector entries are reused across rows)
 __global__ void __launch_bounds__(GV_NT) gemv_rowmajor_kernel(const cplx* __restrict__ A, const cplx* __restrict__ V,
                                                               long long ldv, cplx* __restrict__ Y, long long ldy, int n,
                                                               int c0, int ncand) {
     __shared__ cplx sV[CB][GV_JC];
+    constexpr int GV_ROWS = RPW * (GV_NT / 32);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row_base = blockIdx.x * GV_ROWS;
-    constexpr int RPW = GV_ROWS / (GV_NT / 32);     // rows per warp
+    const int row0 = blockIdx.x * GV_ROWS + warp * RPW;
     cplx acc[RPW][CB];
 #pragma unroll
     for (int r = 0; r < RPW; ++r)
@@ -173,31 +173,39 @@ __global__ void __launch_bounds__(GV_NT) gemv_rowmajor_kernel(const cplx* __rest
             sV[c][j] = (c < ncand) ? V[(long long)(c0 + c) * ldv + j0 + j] : cmake(0.0, 0.0);
         }
         __syncthreads();
+        const cplx* arow[RPW];
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            const int row = row_base + warp * RPW + r;
-            if (row < n) {
-                const cplx* arow = A + (long long)row * n + j0;
-                int j = lane;
-                for (; j + 96 < jc; j += 128) {
-                    cplx a0 = __ldcs(&arow[j]), a1 = __ldcs(&arow[j + 32]), a2 = __ldcs(&arow[j + 64]), a3 = __ldcs(&arow[j + 96]);
+        for (int r = 0; r < RPW; ++r) arow[r] = A + (long long)min(row0 + r, n - 1) * n + j0;   // clamped: extra rows are not stored
+        int j = lane;
+        for (; j + 96 < jc; j += 128) {
+            cplx a[RPW][4];
 #pragma unroll
-                    for (int c = 0; c < CB; ++c) {
-                        cfma(acc[r][c], a0, sV[c][j]); cfma(acc[r][c], a1, sV[c][j + 32]);
-                        cfma(acc[r][c], a2, sV[c][j + 64]); cfma(acc[r][c], a3, sV[c][j + 96]);
-                    }
+            for (int r = 0; r < RPW; ++r) {
+                a[r][0] = __ldcs(&arow[r][j]); a[r][1] = __ldcs(&arow[r][j + 32]);
+                a[r][2] = __ldcs(&arow[r][j + 64]); a[r][3] = __ldcs(&arow[r][j + 96]);
+            }
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+                const cplx v0 = sV[c][j], v1 = sV[c][j + 32], v2 = sV[c][j + 64], v3 = sV[c][j + 96];
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    cfma(acc[r][c], a[r][0], v0); cfma(acc[r][c], a[r][1], v1);
+                    cfma(acc[r][c], a[r][2], v2); cfma(acc[r][c], a[r][3], v3);
                 }
-                for (; j < jc; j += 32) {
-                    cplx a0 = __ldcs(&arow[j]);
+            }
+        }
+        for (; j < jc; j += 32) {
 #pragma unroll
-                    for (int c = 0; c < CB; ++c) cfma(acc[r][c], a0, sV[c][j]);
-                }
+            for (int r = 0; r < RPW; ++r) {
+                const cplx a0 = __ldcs(&arow[r][j]);
+#pragma unroll
+                for (int c = 0; c < CB; ++c) cfma(acc[r][c], a0, sV[c][j]);
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-        const int row = row_base + warp * RPW + r;
+        const int row = row0 + r;
 #pragma unroll
         for (int c = 0; c < CB; ++c) {
             cplx s = warp_sum(acc[r][c]);
@@ -256,14 +264,22 @@ cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int 
     return cudaGetLastError();
 }
 
-cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
-                              cudaStream_t stream) {
-    const int grid = (n + GV_ROWS - 1) / GV_ROWS;
+template <int RPW>
+static void gemv_launch(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C, cudaStream_t stream) {
+    const int rows = RPW * (GV_NT / 32);
+    const int grid = (n + rows - 1) / rows;
     for (int c0 = 0; c0 < C; c0 += 4) {
         const int nc = (C - c0 < 4) ? (C - c0) : 4;
-        if (nc == 1) gemv_rowmajor_kernel<1><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
-        else if (nc == 2) gemv_rowmajor_kernel<2><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
-        else gemv_rowmajor_kernel<4><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
+        if (nc == 1) gemv_rowmajor_kernel<1, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
+        else if (nc == 2) gemv_rowmajor_kernel<2, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
+        else gemv_rowmajor_kernel<4, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
     }
+}
+
+cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
+                              cudaStream_t stream) {
+    // grid sized so that several waves of CTAs cover the 148 SMs: 8 rows per CTA below n = 8192, 16 above
+    if (n >= 8192) gemv_launch<2>(A_rm, V, ldv, Y, ldy, n, C, stream);
+    else gemv_launch<1>(A_rm, V, ldv, Y, ldy, n, C, stream);
     return cudaGetLastError();
 }
