@@ -126,19 +126,16 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
                     const int sb = (int)(ib % BSTAGES), kb0 = kt * KC;
                     const int kvb = min(KCB, p.K - kb0);
                     if (ib >= BSTAGES) mbar_wait(&bempty[sb], (uint32_t)(((ib / BSTAGES) - 1) & 1));
-                    if (!(p.debug & 1)) {
-                        if (lane == 0) mbar_expect_tx(&bfull[sb], (uint32_t)(cols_valid * kvb * sizeof(cplx)));
-                        __syncwarp();
-                        cplx* b_s = sB + sb * B_STAGE;
-                        for (int j = lane; j < cols_valid; j += 32)
-                            bulk_g2s(b_s + j * LDSB, B + kb0 + (long long)(n0 + j) * p.ldb, (uint32_t)(kvb * sizeof(cplx)), &bfull[sb]);
-                    } else if (lane == 0) mbar_arrive(&bfull[sb]);
+                    if (lane == 0) mbar_expect_tx(&bfull[sb], (uint32_t)(cols_valid * kvb * sizeof(cplx)));
+                    __syncwarp();
+                    cplx* b_s = sB + sb * B_STAGE;
+                    for (int j = lane; j < cols_valid; j += 32)
+                        bulk_g2s(b_s + j * LDSB, B + kb0 + (long long)(n0 + j) * p.ldb, (uint32_t)(kvb * sizeof(cplx)), &bfull[sb]);
                     ++ib;
                 }
                 const int s = (int)(it % STAGES), k0 = kt * KC;
                 const int kv = min(KC, p.K - k0);
                 if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
-                if (p.debug & 1) { if (lane == 0) mbar_arrive(&full[s]); continue; }
                 if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(kv * rows_valid * sizeof(cplx)));
                 __syncwarp();
                 if (lane < kv)
@@ -166,7 +163,7 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
         double acc[AB][4][2];
         const int crow = m0 + wm * (8 * AB) + g;       // + 8*qa
         const int ccol = n0 + wn * 16 + t;             // + 4*qb
-        if (p.beta && !(p.debug & 16)) {
+        if (p.beta) {
             // accumulators start from C (L2 hits: the producer prefetched this tile while the previous one was computed)
 #pragma unroll
             for (int qa = 0; qa < AB; ++qa)
@@ -194,10 +191,9 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
             const int s = (int)(it % STAGES);
             const int kv = min(KC, p.K - kt * KC);
             const int kboff = (kt % APB) * KC;       // offset of this A slab inside the B slab
-            if (!(p.debug & 8)) mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+            mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
             const double* a_s = reinterpret_cast<const double*>(sA + s * A_STAGE);
-            if (p.debug & 2) {
-            } else if (kv == KC) {
+            if (kv == KC) {
 #pragma unroll
                 for (int ks = 0; ks < KC / 2; ++ks) {
                     const int kc = 2 * ks + kh;
@@ -235,13 +231,12 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
                 if (kt % APB == APB - 1 || kt == KT - 1) mbar_arrive(&bempty[sb]);
             }
         }
-        if (p.debug & 4) { if (acc[0][0][0] == 1.2345e-300) C[0] = cmake(acc[1][1][0], acc[2][2][1]); continue; }
 #pragma unroll
         for (int qa = 0; qa < AB; ++qa)
 #pragma unroll
             for (int qb = 0; qb < 4; ++qb) {
                 int r = crow + 8 * qa, c = ccol + 4 * qb;
-                if (r < p.M && c < p.N && !((p.debug & 32) && acc[qa][qb][0] != 1.2345e-300)) C[r + (long long)c * p.ldc] = cmake(acc[qa][qb][0], acc[qa][qb][1]);
+                if (r < p.M && c < p.N) C[r + (long long)c * p.ldc] = cmake(acc[qa][qb][0], acc[qa][qb][1]);
             }
     }
 }
@@ -302,7 +297,6 @@ cudaError_t zgemm_dmma_launch(const ZgemmParams& p, cudaStream_t stream) {
         const char* e = getenv("MAUS_GEMM_CFG");
         g_zgemm_cfg = e ? atoi(e) : 0;
     }
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MAUS_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; } const_cast<ZgemmParams&>(p).debug = dbg; }
     if ((const void*)p.C == (const void*)p.B) return launch_cfg<128, 8>(p, stream);   // in-place (U12 = L11^-1 A12): one row tile must own all rows
     if (g_zgemm_cfg == 1) return launch_cfg<128, 4>(p, stream);
     if (g_zgemm_cfg == 3) return launch_cfg<64, 8>(p, stream);   // 64 x 64 tiles, 2 CTAs / SM

@@ -9,7 +9,6 @@ struct ZgemmParams {
     int M, N, K, batch;
     int beta;      // 0: C = s*A*B        1: C = C + s*A*B
     int negate;    // s = -1 when set, else +1
-    int debug;     // experiments only: bit0 = producer skips the copies, bit1 = consumers skip the MMAs
 };
 
 // Tensor-pipe kernel (any M, N, K >= 1).  In-place use (C == B) is supported for M <= 128: it is routed to the 128-row tile configuration so one CTA owns all rows of its columns.

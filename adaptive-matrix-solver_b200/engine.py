@@ -74,6 +74,14 @@ class MausEngine:
         buf = (C.c_char * max(nbytes, 16)).from_address(p)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
+    def staging(self, shape):
+        """Reusable page-locked [C][n] complex128 buffer for the per-step host<->device copies of the candidate vectors."""
+        need = int(np.prod(shape))
+        buf = getattr(self, "_staging", None)
+        if buf is None or buf.size < need:
+            buf = self._staging = self.pinned_empty((max(need, 1),))
+        return buf[:need].reshape(shape)
+
     @property
     def stream_ptr(self):
         """cudaStream_t of the context (int), e.g. for torch.cuda.ExternalStream"""

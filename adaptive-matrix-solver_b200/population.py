@@ -155,7 +155,8 @@ def step_population(candidates, M, b, strat_params, problem_knowledge, engine, c
 def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, res_slot):
     C_ = len(cands)
     eigen = ptype == _abi.EIGENVALUE
-    V = np.empty((C_, N), dtype=np.complex128)
+    # the vectors travel through one page-locked staging buffer (H2D before, D2H after the fused step)
+    V = engine.staging((C_, N)) if hasattr(engine, "staging") else np.empty((C_, N), dtype=np.complex128)
     for i, c in enumerate(cands):
         if eigen:
             if np.linalg.norm(c.v_k) < 1e-10:                                                  # AMS:259-263
