@@ -63,9 +63,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+// L2 policies: the A / B panels are re-read by many tiles (keep), the C tiles stream through once (do not keep)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ cplx ld_stream(const cplx* p, uint64_t policy) {
+    cplx v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void st_stream(cplx* p, cplx v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -103,6 +118,7 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
     if (warp == NCONS) {
         // ---------------- producer warp: TMA bulk copies, one per contiguous column segment ----------------
         long long it = 0, ib = 0;
+        const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int mt = (int)(tile % tiles_m), nt = (int)((tile / tiles_m) % tiles_n), bz = (int)(tile / ((long long)tiles_m * tiles_n));
             const int m0 = mt * TM, n0 = nt * TN;
@@ -117,8 +133,8 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
                     const cplx* C2 = p.C + (long long)bz2 * p.strideC + mt2 * TM + (long long)(nt2 * TN) * p.ldc;
                     const int rv = min(TM, p.M - mt2 * TM), cvn = min(TN, p.N - nt2 * TN);
                     for (int j = lane; j < cvn; j += 32)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(C2 + (long long)j * p.ldc),
-                                     "r"((uint32_t)(rv * sizeof(cplx))) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(C2 + (long long)j * p.ldc),
+                                     "r"((uint32_t)(rv * sizeof(cplx))), "l"(stream) : "memory");
                 }
             }
             for (int kt = 0; kt < KT; ++kt, ++it) {
@@ -130,7 +146,7 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
                     __syncwarp();
                     cplx* b_s = sB + sb * B_STAGE;
                     for (int j = lane; j < cols_valid; j += 32)
-                        bulk_g2s(b_s + j * LDSB, B + kb0 + (long long)(n0 + j) * p.ldb, (uint32_t)(kvb * sizeof(cplx)), &bfull[sb]);
+                        bulk_g2s(b_s + j * LDSB, B + kb0 + (long long)(n0 + j) * p.ldb, (uint32_t)(kvb * sizeof(cplx)), &bfull[sb], keep);
                     ++ib;
                 }
                 const int s = (int)(it % STAGES), k0 = kt * KC;
@@ -140,7 +156,7 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
                 __syncwarp();
                 if (lane < kv)
                     bulk_g2s(sA + s * A_STAGE + lane * LDSA, A + m0 + (long long)(k0 + lane) * p.lda,
-                             (uint32_t)(rows_valid * sizeof(cplx)), &full[s]);
+                             (uint32_t)(rows_valid * sizeof(cplx)), &full[s], keep);
             }
         }
         return;
@@ -156,6 +172,7 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
     const int arow = wm * (8 * AB) + g;
     const int bcol = wn * 16 + (g >> 1);
     long long it = 0, ib = 0;
+    const uint64_t stream = l2_policy_evict_first();
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int mt = (int)(tile % tiles_m), nt = (int)((tile / tiles_m) % tiles_n), bz = (int)(tile / ((long long)tiles_m * tiles_n));
         const int m0 = mt * TM, n0 = nt * TN;
@@ -170,7 +187,7 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
 #pragma unroll
                 for (int qb = 0; qb < 4; ++qb) {
                     int r = crow + 8 * qa, c = ccol + 4 * qb;
-                    cplx v = (r < p.M && c < p.N) ? __ldcg(&C[r + (long long)c * p.ldc]) : cmake(0.0, 0.0);
+                    cplx v = (r < p.M && c < p.N) ? ld_stream(&C[r + (long long)c * p.ldc], stream) : cmake(0.0, 0.0);
                     acc[qa][qb][0] = v.x; acc[qa][qb][1] = v.y;
                 }
         } else {
@@ -236,7 +253,7 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
 #pragma unroll
             for (int qb = 0; qb < 4; ++qb) {
                 int r = crow + 8 * qa, c = ccol + 4 * qb;
-                if (r < p.M && c < p.N) C[r + (long long)c * p.ldc] = cmake(acc[qa][qb][0], acc[qa][qb][1]);
+                if (r < p.M && c < p.N) st_stream(&C[r + (long long)c * p.ldc], cmake(acc[qa][qb][0], acc[qa][qb][1]), stream);
             }
     }
 }

@@ -79,6 +79,43 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def lu_gemm_algorithmic(n, cand, nb=128, group=4):
+    """(launches, flops, bytes) of the GEMM launches of ONE batched LU generation, following the schedule of
+    maus_lu_solve (csrc/maus_api.cu): per launch bytes = C read (beta = 1) + C write + A + B, complex128."""
+    launches, flops, byts = 0, 0.0, 0.0
+
+    def g(M, N, K, beta):
+        nonlocal launches, flops, byts
+        if M <= 0 or N <= 0:
+            return
+        launches += 1
+        flops += 8.0 * M * N * K * cand
+        byts += 16.0 * cand * (M * N * (1 + beta) + M * K + K * N)
+    k0 = 0
+    while k0 < n:
+        kend = min(n, k0 + group * nb)
+        nc_out = n + 1 - kend
+        kp = k0
+        while kp < kend:
+            jb = min(nb, kend - kp)
+            kq = kp + jb
+            if kp > k0 and nc_out > 0:
+                g(jb, nc_out, kp - k0, 1)
+            g(jb, n + 1 - kq, jb, 0)
+            if n - kq > 0 and kend - kq > 0:
+                g(n - kq, kend - kq, jb, 1)
+            kp = kq
+        if n - kend > 0 and nc_out > 0:
+            g(n - kend, nc_out, kend - k0, 1)
+        k0 = kend
+    return launches, flops, byts
+
+
+# DRAM traffic of the LU GEMM launches measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum over the 87 launches
+# of one generation at n = 4096 with 16 candidates: profiles/gemm_traffic_r01_c16.csv), per candidate
+NCU_GEMM_DRAM_BYTES_PER_CANDIDATE = (31.32e9 + 12.98e9) / 16.0
+
+
 def vector_alpha_update(alpha, resid, prev):
     """AMS:306-316 vectorised over the shard (frozen population: the convergence stop AMS:318-331 is not applied)."""
     a = alpha.copy()
@@ -191,9 +228,15 @@ def run_b200(args):
     # ------------------------------------------------------------------ roofline of the dominant kernel
     gemm_s = prof["lu_gemm_ms"] / 1e3
     achieved = prof["lu_gemm_flops"] / gemm_s / 1e12 if gemm_s > 0 else 0.0
+    n_launch, alg_flops, alg_bytes = lu_gemm_algorithmic(n, C_)
+    per_launch = max(1, prof["lu_gemm_launches"] // args.steps)
     roofline = {"kernel": "zgemm_dmma_kernel (LU trailing update + U12 solve)", "bound": "tensor",
                 "achieved": round(achieved, 3), "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": round(achieved / FP64_PEAK_TFLOPS, 4), "traffic": None,
+                "frac": round(achieved / FP64_PEAK_TFLOPS, 4),
+                "traffic": round(NCU_GEMM_DRAM_BYTES_PER_CANDIDATE * C_ / per_launch) if n == 4096 else None,
+                "traffic_unit": "bytes per launch (ncu dram read+write, average over the LU GEMM launches of a generation; "
+                                "measured at 16 candidates and scaled by the candidate count, profiles/gemm_traffic_r01_c16.csv)",
+                "algorithmic_flops_per_launch": round(alg_flops / n_launch), "algorithmic_bytes_per_launch": round(alg_bytes / n_launch),
                 "peak_source": "own measurement (FP64 DMMA, profiles/fp64_peak_r01.txt); MEASURED_PEAKS.json has no FP64 entry",
                 "share_of_step": round(gemm_s / (dev_ms / 1e3), 4) if dev_ms > 0 else None,
                 "launches": prof["lu_gemm_launches"],
