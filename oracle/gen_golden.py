@@ -34,6 +34,9 @@ def snap(c):
     return dict(
         lam=complex(c.lambda_k) if c.lambda_k is not None else complex("nan"),
         v=None if c.v_k is None else np.array(c.v_k, dtype=np.complex128, copy=True),
+        u=None if getattr(c, "u_k", None) is None else np.array(c.u_k, dtype=np.complex128, copy=True),
+        rv=None if getattr(c, "right_v_k", None) is None else np.array(c.right_v_k, dtype=np.complex128, copy=True),
+        sigma=float(np.real(c.sigma_k)) if getattr(c, "sigma_k", None) is not None else float("nan"),
         x=None if c.x_k is None else np.array(c.x_k, dtype=np.complex128, copy=True),
         state=int(c.state.value), w=float(c.w_k), res=float(c.residual_k), prev=float(c.prev_residual),
         alpha=complex(al), alpha_is_complex=bool(isinstance(al, (complex, np.complexfloating))),
@@ -78,7 +81,7 @@ def _pack(vecs, n):
 
 
 def save(name, records, A, b, A_ctor, meta):
-    n = A.shape[0]
+    n = A.shape[0] if meta.get("problem_type") != 3 else max(A.shape)
     arrs = {}
     if sp.issparse(A):
         Ac = sp.csc_matrix(A)
@@ -94,6 +97,10 @@ def save(name, records, A, b, A_ctor, meta):
     for side in ("before", "after"):
         arrs[f"{side}_v"] = _pack([r[side]["v"] for r in records], n)
         arrs[f"{side}_x"] = _pack([r[side]["x"] for r in records], n)
+        if meta.get("problem_type") == 3:
+            arrs[f"{side}_u"] = _pack([r[side]["u"] for r in records], A.shape[0])
+            arrs[f"{side}_rv"] = _pack([r[side]["rv"] for r in records], A.shape[1])
+            arrs[f"{side}_sigma"] = np.array([r[side]["sigma"] for r in records], dtype=np.float64)
         arrs[f"{side}_lam"] = np.array([r[side]["lam"] for r in records], dtype=np.complex128)
         arrs[f"{side}_alpha"] = np.array([r[side]["alpha"] for r in records], dtype=np.complex128)
         for k in ("w", "res", "prev"):
@@ -205,5 +212,21 @@ def main():
     save("fail6", recs, s.M, None, A, dict(problem_type=1, gmres_mode="shim", **versions()))
 
 
+def svd_golden():
+    """svd5x4 -- AMS:662-665 scenario 3 (near-low-rank 5 x 4) and a 40 x 28 variant; SVD power-sweep branch."""
+    shim = load_reference(gmres_shim=True, name="ams_svd")
+    for tag, (mr, mc, ncand, gens) in {"svd5x4": (5, 4, 25, 12), "svd40x28": (40, 28, 12, 6)}.items():
+        np.random.seed(SEED + 6 + mr); random.seed(SEED + 6 + mr)
+        M = shim.create_low_rank_svd_matrix_for_MAUS(mr, mc, target_rank=2)
+        s = quiet(shim.MAUS_Solver, M, problem_type=shim.ProblemType.SVD, initial_num_candidates=ncand,
+                  global_convergence_tol=1e-6)
+        recs = run_maus(shim, s, gens, (lambda i, sv: True) if mr < 10 else (lambda i, sv: i % 5 == 0))
+        save(tag, recs, s.M, None, None, dict(problem_type=3, gmres_mode="shim", **versions()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "svd":
+        svd_golden()
+    else:
+        main()
+        svd_golden()

@@ -2,7 +2,8 @@
 
 This file is a numpy/scipy *restatement* of the reference's algorithm for ONE path: the per-candidate
 Psi-regularised shifted inverse-iteration step (``InverseIterateSolver.solve`` + the eigen / linear-system
-branch of ``SolutionCandidate.update_solution_step``).  AMS = /root/reference/Adaptive_Matrix_Solver_0.1.py.
+branch of ``SolutionCandidate.update_solution_step``, plus the SVD power sweep
+of the same method -- the first 'next' row of SURVEY.md section 8f).  AMS = /root/reference/Adaptive_Matrix_Solver_0.1.py.
 It is the checker for the CUDA path; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs may import it.  The product package never does.
 
@@ -32,6 +33,7 @@ PSI_EPSILON_BASE = np.complex128(1e-20)      # AMS:16
 ALPHA_V_INITIAL = np.complex128(0.01)        # AMS:17
 MAX_PSI_ATTEMPTS = 25                        # AMS:18
 MAX_STUCK_FOR_RETIREMENT = 8                 # AMS:19
+SIGMA_SIMILARITY_TOL_ABS = 1e-6              # AMS:23
 CONVERGENCE_RESIDUAL_TOL = 1e-8              # AMS:25
 
 # problem types (AMS:10-13) and candidate states (AMS:109-110) as plain ints
@@ -120,6 +122,11 @@ class CandState:
     w_k: float = 0.01
     residual_k: float = float("inf")
     prev_residual: float = float("inf")
+    u_k: object = None
+    right_v_k: object = None
+    sigma_k: object = None
+    M_rows: int = 0
+    M_cols: int = 0
     alpha_local_step: object = ALPHA_V_INITIAL
     stuck_counter: int = 0
     local_psi_retries_needed: int = 0
@@ -133,6 +140,10 @@ class CandState:
             c.v_k = np.array(c.v_k, copy=True)
         if c.x_k is not None:
             c.x_k = np.array(c.x_k, copy=True)
+        if c.u_k is not None:
+            c.u_k = np.array(c.u_k, copy=True)
+        if c.right_v_k is not None:
+            c.right_v_k = np.array(c.right_v_k, copy=True)
         return c
 
 
@@ -154,6 +165,10 @@ def initialize_random_solution(c):
         c.lambda_k = (_pyrandom.random() * 5 - 2.5 + 1j * (_pyrandom.random() * 5 - 2.5))
     elif c.problem_type == SOLVE_LINEAR_SYSTEM:
         c.x_k = _norm_rand_vec(_rand_vec_init(c.N)) * _pyrandom.uniform(0.1, 10.0)
+    elif c.problem_type == SVD:
+        c.u_k = _norm_rand_vec(_rand_vec_init(c.M_rows))
+        c.right_v_k = _norm_rand_vec(_rand_vec_init(c.M_cols))
+        c.sigma_k = 1.0
     c.history_len += 1
 
 
@@ -176,7 +191,12 @@ def adapt_alpha_and_state(c):
 
 def convergence_test(c, current_conv_tol):
     """AMS:318-331."""
-    params = (c.lambda_k, c.v_k) if c.problem_type == EIGENVALUE else (c.x_k,)
+    if c.problem_type == EIGENVALUE:
+        params = (c.lambda_k, c.v_k)
+    elif c.problem_type == SOLVE_LINEAR_SYSTEM:
+        params = (c.x_k,)
+    else:
+        params = (c.sigma_k, c.u_k, c.right_v_k)
     finite = True
     for p in params:
         if p is None:
@@ -208,6 +228,8 @@ def candidate_step(c, current_matrix_A, b_vector, strat_params, global_knowledge
     pref = global_knowledge.get("local_solver_preference", "direct_solve")
     is_sparse = global_knowledge.get("is_sparse_problem", False)
     N = c.N
+    if c.problem_type == SVD:
+        return _svd_step(c, current_matrix_A, A_res_calc, strat_params)
     solver_kw = dict(N=N, base_psi_epsilon=PSI_EPSILON_BASE * aggr, max_attempts=max_retries,
                      preferred_method=pref, is_sparse=is_sparse, gmres_mode=gmres_mode, rand=rand, trace=trace)
 
@@ -260,6 +282,57 @@ def candidate_step(c, current_matrix_A, b_vector, strat_params, global_knowledge
     else:
         c.residual_k = np.linalg.norm(A_res_calc @ c.x_k - b_vector)
     c.history_len += 1                                                                         # AMS:303-304
+    adapt_alpha_and_state(c)
+    convergence_test(c, strat_params.get("current_convergence_threshold", CONVERGENCE_RESIDUAL_TOL))
+    return c
+
+
+def _svd_step(c, A, A_res_calc, strat_params):
+    """SVD branch of update_solution_step: one power sweep u = Av/||.||, v = A^H u/||.|| (AMS:227-255), residual
+    (AMS:300-301), then the common tail (AMS:303-331).  Never calls the inverse-iteration solver."""
+    Mr, Mc = c.M_rows, c.M_cols
+    try:
+        if np.linalg.norm(c.right_v_k) < 1e-10:                                                 # AMS:229-232
+            c.right_v_k = (np.random.rand(Mc) + 1j * np.random.rand(Mc))
+            c.right_v_k /= np.linalg.norm(c.right_v_k)
+            c.stuck_counter += 1
+            c.num_resets += 1
+            raise ValueError("SVD right_v_k collapsed.")
+        temp_u_k = A @ c.right_v_k                                                              # AMS:233
+        c.sigma_k = np.linalg.norm(temp_u_k)
+        c.u_k = temp_u_k / (c.sigma_k if c.sigma_k > 1e-10 else 1.0)
+        if np.linalg.norm(c.u_k) < 1e-10:                                                       # AMS:236-239
+            c.u_k = (np.random.rand(Mr) + 1j * np.random.rand(Mr))
+            c.u_k /= np.linalg.norm(c.u_k)
+            c.stuck_counter += 1
+            c.num_resets += 1
+            raise ValueError("SVD u_k collapsed.")
+        temp_v_k = A.conj().T @ c.u_k                                                           # AMS:240
+        c.sigma_k = max(c.sigma_k, np.linalg.norm(temp_v_k))
+        c.right_v_k = temp_v_k / (np.linalg.norm(temp_v_k) if np.linalg.norm(temp_v_k) > 1e-10 else 1.0)
+        if c.sigma_k < SIGMA_SIMILARITY_TOL_ABS / 100:                                          # AMS:243-247
+            c.residual_k = strat_params.get("current_convergence_threshold", 1e-6) * 0.1
+            c.state = CONVERGED
+            c.stuck_counter = 0
+            if np.linalg.norm(c.u_k) < 1e-10:
+                c.u_k = np.ones(Mr, dtype=np.complex128) / np.sqrt(Mr)
+            if np.linalg.norm(c.right_v_k) < 1e-10:
+                c.right_v_k = np.ones(Mc, dtype=np.complex128) / np.sqrt(Mc)
+        else:
+            c.stuck_counter = max(0, c.stuck_counter - 1)                                       # AMS:248
+    except (RuntimeError, ValueError, np.linalg.LinAlgError):                                   # AMS:249-255
+        c.stuck_counter += 1
+        c.w_k *= 0.001
+        c.alpha_local_step *= 0.5
+        c.state = STUCK
+        if c.stuck_counter >= MAX_STUCK_FOR_RETIREMENT:
+            c.state = RETIRED
+        c.u_k = (np.random.rand(Mr) + 1j * np.random.rand(Mr)) / np.sqrt(Mr)
+        c.right_v_k = (np.random.rand(Mc) + 1j * np.random.rand(Mc)) / np.sqrt(Mc)
+        c.sigma_k = 1.0
+    c.residual_k = (np.linalg.norm(A_res_calc @ c.right_v_k - c.sigma_k * c.u_k)
+                    + np.linalg.norm(A_res_calc.conj().T @ c.u_k - c.sigma_k * c.right_v_k))    # AMS:301
+    c.history_len += 1
     adapt_alpha_and_state(c)
     convergence_test(c, strat_params.get("current_convergence_threshold", CONVERGENCE_RESIDUAL_TOL))
     return c

@@ -6,7 +6,7 @@ import numpy as np
 import scipy.sparse as sp
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["eig8", "eig100", "lin5_shim", "lin5_shipped", "gmres64", "speig200", "fail6"]
+NAMES = ["eig8", "eig100", "lin5_shim", "lin5_shipped", "gmres64", "speig200", "fail6", "svd5x4", "svd40x28"]
 
 
 class Golden:
@@ -44,7 +44,10 @@ class Golden:
         alpha = g("alpha")
         alpha = np.complex128(alpha) if g("alpha_is_complex") else float(alpha.real)
         v = g("v"); x = g("x")
-        return dict(lam=complex(g("lam")), v=None if np.isnan(v).all() and self.problem_type == 2 else v,
+        extra = {}
+        if self.problem_type == 3:
+            extra = dict(u=g("u")[:self.A.shape[0]].copy(), rv=g("rv")[:self.A.shape[1]].copy(), sigma=float(g("sigma")))
+        return dict(**extra, lam=complex(g("lam")), v=None if np.isnan(v).all() and self.problem_type != 1 else v,
                     x=None if np.isnan(x).all() and self.problem_type == 1 else x,
                     state=int(g("state")), w=float(g("w")), res=float(g("res")), prev=float(g("prev")),
                     alpha=alpha, stuck=int(g("stuck")), retries=int(g("retries")), resets=int(g("resets")),

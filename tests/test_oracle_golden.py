@@ -20,6 +20,10 @@ def _make_state(g, i):
     c.state = s["state"]; c.w_k = s["w"]; c.residual_k = s["res"]; c.prev_residual = s["prev"]
     c.alpha_local_step = s["alpha"]; c.stuck_counter = s["stuck"]; c.local_psi_retries_needed = s["retries"]
     c.num_resets = s["resets"]; c.history_len = s["hist"]
+    if g.problem_type == 3:
+        c.M_rows, c.M_cols = g.A.shape
+        c.u_k = s["u"].copy(); c.right_v_k = s["rv"].copy(); c.sigma_k = s["sigma"]
+        c.v_k = None; c.x_k = None
     return c
 
 
@@ -61,8 +65,11 @@ def test_oracle_replays_reference_steps(name):
             if g.problem_type == 1:
                 assert _close(c.lambda_k, a["lam"], rtol), (name, i, c.lambda_k, a["lam"])
                 assert _close(c.v_k, a["v"], 1e-9), (name, i)
-            else:
+            elif g.problem_type == 2:
                 assert _close(c.x_k, a["x"], 1e-9), (name, i)
+            else:
+                assert _close(float(np.real(c.sigma_k)), a["sigma"], rtol), (name, i)
+                assert _close(c.u_k, a["u"], 1e-9) and _close(c.right_v_k, a["rv"], 1e-9), (name, i)
 
 
 def test_psi_magnitude_matches_reference_formula():
