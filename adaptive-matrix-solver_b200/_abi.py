@@ -9,7 +9,7 @@ LIB_NAME = "libmaus_b200.so"
 
 # status words / enums of include/maus_b200.h
 ST_OK, ST_ZERO_PIVOT, ST_NONFINITE, ST_GMRES_NOCONV, ST_V_COLLAPSED, ST_MIX_COLLAPSED, ST_SKIPPED = range(7)
-EIGENVALUE, SOLVE_LINEAR_SYSTEM = 1, 2
+EIGENVALUE, SOLVE_LINEAR_SYSTEM, SVD = 1, 2, 3
 METHOD_LU, METHOD_GMRES = 0, 1
 SLOT_CURRENT, SLOT_CTOR = 0, 1
 
@@ -17,7 +17,7 @@ EXPORTS = [
     "maus_create", "maus_destroy", "maus_last_error", "maus_set_workspace_limit", "maus_info", "maus_alloc_pinned",
     "maus_free_pinned", "maus_set_dense", "maus_set_csc", "maus_set_rhs", "maus_upload_vectors",
     "maus_download_vectors", "maus_download_vector_range", "maus_rq", "maus_solve_shifted", "maus_solve_with_R", "maus_mix_residual",
-    "maus_residual", "maus_step", "maus_launch_count", "maus_profile_reset", "maus_profile_read", "maus_profile_read_kind", "maus_stream", "maus_debug_zgemm",
+    "maus_residual", "maus_step", "maus_launch_count", "maus_profile_reset", "maus_profile_read", "maus_profile_read_kind", "maus_stream", "maus_debug_zgemm", "maus_svd_set_matrix", "maus_svd_step", "maus_svd_residual",
 ]
 
 
@@ -80,6 +80,9 @@ def load_library():
         "maus_profile_read_kind": (i32, [vp, i32, dp, i64p, dp]),
         "maus_stream": (vp, [vp]),
         "maus_debug_zgemm": (i32, [vp, i32, i32, i32, i32, dp, dp, dp, i32, i32, i32]),
+        "maus_svd_set_matrix": (i32, [vp, i64, i64, dp]),
+        "maus_svd_step": (i32, [vp, i64, dp, dp, dp, dp, i32p]),
+        "maus_svd_residual": (i32, [vp, i64, dp, dp, dp, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError if the .so does not export it

@@ -5,6 +5,7 @@ PSI_EPSILON_BASE = np.complex128(1e-20)       # GLOBAL_DEFAULT_PSI_EPSILON_BASE,
 ALPHA_V_INITIAL = np.complex128(0.01)         # GLOBAL_DEFAULT_ALPHA_V_INITIAL, AMS:17
 MAX_PSI_ATTEMPTS = 25                         # GLOBAL_MAX_PSI_ATTEMPTS, AMS:18
 MAX_STUCK_FOR_RETIREMENT = 8                  # GLOBAL_MAX_STUCK_FOR_RETIREMENT, AMS:19
+SIGMA_SIMILARITY_TOL_ABS = 1e-6               # GLOBAL_SIGMA_SIMILARITY_TOL_ABS, AMS:23
 CONVERGENCE_RESIDUAL_TOL = 1e-8               # GLOBAL_CONVERGENCE_RESIDUAL_TOL, AMS:25
 LU_MAX_N = 8192                               # largest order the batched LU accepts (csrc/lu.cuh)
 

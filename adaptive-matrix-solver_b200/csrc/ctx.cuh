@@ -61,6 +61,8 @@ struct maus_ctx {
 
     // GMRES workspace (gmres.cu)
     void* gmres = nullptr;
+    // SVD branch (svd.cu): rectangular matrix in four layouts + candidate buffers
+    void* svd = nullptr;
 
     long long launches = 0;
     long long bytes_held = 0;
@@ -94,3 +96,4 @@ int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double
                      const unsigned char* use_jacobi, const cplx* rhs, long long rhs_stride, cplx* X, int* status,
                      int* iters, double max_psi_host);
 void maus_gmres_free(maus_ctx* ctx);
+void maus_svd_free(maus_ctx* ctx);

@@ -154,8 +154,9 @@ __global__ void __launch_bounds__(RED_NT) nan_scan_kernel(const cplx* __restrict
 constexpr int GV_NT = 256, GV_JC = 512;
 template <int CB, int RPW>      // CB candidates per pass, RPW rows per warp (the staged vector entries are reused across rows)
 __global__ void __launch_bounds__(GV_NT) gemv_rowmajor_kernel(const cplx* __restrict__ A, const cplx* __restrict__ V,
-                                                              long long ldv, cplx* __restrict__ Y, long long ldy, int n,
-                                                              int c0, int ncand) {
+                                                              long long ldv, cplx* __restrict__ Y, long long ldy, int nrows,
+                                                              int n, int c0, int ncand) {
+    // A is nrows x n row-major; Y[c] (nrows) = A * V[c] (n)
     __shared__ cplx sV[CB][GV_JC];
     constexpr int GV_ROWS = RPW * (GV_NT / 32);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(GV_NT) gemv_rowmajor_kernel(const cplx* __rest
         __syncthreads();
         const cplx* arow[RPW];
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) arow[r] = A + (long long)min(row0 + r, n - 1) * n + j0;   // clamped: extra rows are not stored
+        for (int r = 0; r < RPW; ++r) arow[r] = A + (long long)min(row0 + r, nrows - 1) * n + j0;   // clamped: extra rows are not stored
         int j = lane;
         for (; j + 96 < jc; j += 128) {
             cplx a[RPW][4];
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(GV_NT) gemv_rowmajor_kernel(const cplx* __rest
 #pragma unroll
         for (int c = 0; c < CB; ++c) {
             cplx s = warp_sum(acc[r][c]);
-            if (lane == 0 && row < n && c < ncand) Y[(long long)(c0 + c) * ldy + row] = s;
+            if (lane == 0 && row < nrows && c < ncand) Y[(long long)(c0 + c) * ldy + row] = s;
         }
     }
 }
@@ -265,21 +266,29 @@ cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int 
 }
 
 template <int RPW>
-static void gemv_launch(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C, cudaStream_t stream) {
+static void gemv_launch(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int nrows, int n, int C,
+                        cudaStream_t stream) {
     const int rows = RPW * (GV_NT / 32);
-    const int grid = (n + rows - 1) / rows;
+    const int grid = (nrows + rows - 1) / rows;
     for (int c0 = 0; c0 < C; c0 += 4) {
         const int nc = (C - c0 < 4) ? (C - c0) : 4;
-        if (nc == 1) gemv_rowmajor_kernel<1, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
-        else if (nc == 2) gemv_rowmajor_kernel<2, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
-        else gemv_rowmajor_kernel<4, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, n, c0, nc);
+        if (nc == 1) gemv_rowmajor_kernel<1, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, nrows, n, c0, nc);
+        else if (nc == 2) gemv_rowmajor_kernel<2, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, nrows, n, c0, nc);
+        else gemv_rowmajor_kernel<4, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, nrows, n, c0, nc);
     }
 }
 
 cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
                               cudaStream_t stream) {
     // grid sized so that several waves of CTAs cover the 148 SMs: 8 rows per CTA below n = 8192, 16 above
-    if (n >= 8192) gemv_launch<2>(A_rm, V, ldv, Y, ldy, n, C, stream);
-    else gemv_launch<1>(A_rm, V, ldv, Y, ldy, n, C, stream);
+    if (n >= 8192) gemv_launch<2>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
+    else gemv_launch<1>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
+    return cudaGetLastError();
+}
+
+cudaError_t vec_gemv_rect(const cplx* A_rm, int nrows, int ncols, const cplx* V, long long ldv, cplx* Y, long long ldy, int C,
+                          cudaStream_t stream) {
+    if (nrows >= 8192) gemv_launch<2>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
+    else gemv_launch<1>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
     return cudaGetLastError();
 }

@@ -27,3 +27,7 @@ cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cp
 
 // diag[i] = A[i][i]; *amax = max_ij (|re| + |im|)  (amax must be zero-initialised)
 cudaError_t vec_diag_amax(const cplx* A_rm, int n, cplx* diag, double* amax, cudaStream_t stream);
+
+// Y[c] (nrows) = A (nrows x ncols, row-major) * V[c] (ncols): rectangular variant for the SVD sweep
+cudaError_t vec_gemv_rect(const cplx* A_rm, int nrows, int ncols, const cplx* V, long long ldv, cplx* Y, long long ldy, int C,
+                          cudaStream_t stream);

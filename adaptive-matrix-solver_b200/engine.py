@@ -247,6 +247,33 @@ class MausEngine:
                                                1 if negate else 0, 1 if use_dmma else 0))
         return Cm
 
+    # -- SVD power-sweep branch (AMS:227-255, 300-301) -------------------------------------------------------
+    def svd_set_matrix(self, A):
+        A = _as_c128(A)
+        if A.ndim != 2:
+            raise ValueError("2-D matrix required")
+        self.svd_shape = A.shape
+        self._check(self._lib.maus_svd_set_matrix(self._h, A.shape[0], A.shape[1], _dp(A)))
+
+    def svd_step(self, U, V):
+        """U [C][rows], V [C][cols] complex128 C-contiguous, updated in place. Returns dict(sigma, resid, status)."""
+        C_ = U.shape[0]
+        rows, cols = self.svd_shape
+        if U.dtype != _c128 or V.dtype != _c128 or not U.flags.c_contiguous or not V.flags.c_contiguous \
+                or U.shape != (C_, rows) or V.shape != (C_, cols):
+            raise ValueError("U [C][rows] / V [C][cols] must be C-contiguous complex128")
+        sigma = np.empty(C_, dtype=np.float64); resid = np.empty(C_, dtype=np.float64); status = np.empty(C_, dtype=np.int32)
+        self._check(self._lib.maus_svd_step(self._h, C_, _dp(U), _dp(V), _dp(sigma), _dp(resid),
+                                            status.ctypes.data_as(C.POINTER(C.c_int32))))
+        return dict(sigma=sigma, resid=resid, status=status)
+
+    def svd_residual(self, U, V, sigma):
+        U = _as_c128(U); V = _as_c128(V)
+        sigma = np.ascontiguousarray(np.atleast_1d(sigma), dtype=np.float64)
+        resid = np.empty(U.shape[0], dtype=np.float64)
+        self._check(self._lib.maus_svd_residual(self._h, U.shape[0], _dp(U), _dp(V), _dp(sigma), _dp(resid)))
+        return resid
+
     # -- fused generation step --------------------------------------------------------------------------------
     def step(self, problem_type, alpha, psi, V=None, rng_key=None, method=_abi.METHOD_LU, use_jacobi=None,
              res_slot=_abi.SLOT_CURRENT, out=None):

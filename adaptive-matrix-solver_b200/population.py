@@ -22,7 +22,7 @@ import numpy as np
 
 from . import _abi
 from .constants import (PSI_EPSILON_BASE, MAX_PSI_ATTEMPTS, MAX_STUCK_FOR_RETIREMENT, CONVERGENCE_RESIDUAL_TOL,
-                        LU_MAX_N, psi_magnitude)
+                        SIGMA_SIMILARITY_TOL_ABS, LU_MAX_N, psi_magnitude)
 from .solver import GpuInverseIterateSolver
 
 _METHOD = {'direct_solve': _abi.METHOD_LU, 'iterative_gmres': _abi.METHOD_GMRES}
@@ -99,16 +99,20 @@ def step_population(candidates, M, b, strat_params, problem_knowledge, engine, c
     State = type(candidates[0]).State
     live = [c for c in candidates if c.state not in (State.CONVERGED, State.RETIRED)]          # AMS:575
     hermitian = bool(problem_knowledge.get('is_hermitian', False))
-    gpu = []
+    gpu, svd = [], []
     for c in live:
         pt = c.problem_type.value
         if pt == _abi.SOLVE_LINEAR_SYSTEM or (pt == _abi.EIGENVALUE and not hermitian):
             gpu.append(c)
+        elif pt == _abi.SVD and hasattr(engine, "svd_step") and c.problem_matrix is M and not _is_sparse(M):
+            svd.append(c)                     # SVD power sweep (AMS:227-255): the first "next" row, SURVEY.md 8f-1
         else:
-            # Hermitian shortcut (AMS:155-221) and SVD sweep (AMS:227-255) are not on the hot path: untouched
+            # Hermitian shortcut (AMS:155-221) is not on the hot path: untouched
             c.update_solution_step(M, b, strat_params, problem_knowledge)
+    if svd:
+        _step_group_svd(svd, M, b, strat_params, engine, State)
     if not gpu:
-        return 0
+        return len(svd)
     cache = cache if cache is not None else getattr(engine, "_matrix_cache", None)
     if cache is None:
         cache = engine._matrix_cache = _MatrixCache()
@@ -228,6 +232,69 @@ def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, 
             vec = c.v_k if eigen else c.x_k
             resid[i] = engine.residual(ptype, vec[None, :], [c.lambda_k] if eigen else None, res_slot=res_slot)[0]
         c.residual_k = np.float64(resid[i])
+        c.param_history.append(c.get_current_solution_params())                                # AMS:303-304
+        c.residual_history.append(c.residual_k)
+        _adapt_and_test(c, State, conv_tol)
+
+
+def _step_group_svd(cands, M, b, strat_params, engine, State):
+    """SVD branch of update_solution_step for a batch (AMS:146-147, 227-255, 300-304, 306-331); the inverse-iteration
+    solver is never called on this branch (the reference only constructs it, AMS:224)."""
+    cache = getattr(engine, "_svd_cache", None)
+    if cache is not M:
+        engine.svd_set_matrix(M)
+        engine._svd_cache = M
+    Mr, Mc = M.shape
+    conv_tol = strat_params.get('current_convergence_threshold', CONVERGENCE_RESIDUAL_TOL)
+    for c in cands:
+        c.b_vector = b
+        c.prev_residual = c.residual_k
+    U = np.ascontiguousarray(np.stack([c.u_k for c in cands]), dtype=np.complex128)
+    V = np.ascontiguousarray(np.stack([c.right_v_k for c in cands]), dtype=np.complex128)
+    out = engine.svd_step(U, V)
+    redo = []
+    for i, c in enumerate(cands):
+        st = int(out["status"][i])
+        failed = False
+        if st == _abi.ST_V_COLLAPSED:                                                           # AMS:229-232
+            c.right_v_k = (np.random.rand(Mc) + 1j * np.random.rand(Mc))
+            c.right_v_k /= np.linalg.norm(c.right_v_k)
+            c.stuck_counter += 1
+            c.num_resets += 1
+            failed = True
+        elif st == _abi.ST_MIX_COLLAPSED:                                                       # AMS:236-239
+            c.u_k = (np.random.rand(Mr) + 1j * np.random.rand(Mr))
+            c.u_k /= np.linalg.norm(c.u_k)
+            c.stuck_counter += 1
+            c.num_resets += 1
+            failed = True
+        else:
+            c.sigma_k = np.float64(out["sigma"][i])                                             # AMS:234, 241
+            c.u_k = U[i].copy()
+            c.right_v_k = V[i].copy()
+            if c.sigma_k < SIGMA_SIMILARITY_TOL_ABS / 100:                                      # AMS:243-247
+                c.state = State.CONVERGED
+                c.stuck_counter = 0
+            else:
+                c.stuck_counter = max(0, c.stuck_counter - 1)                                   # AMS:248
+            c.residual_k = np.float64(out["resid"][i])                                          # AMS:301
+        if failed:                                                                              # AMS:249-255
+            c.stuck_counter += 1
+            c.w_k *= 0.001
+            c.alpha_local_step *= 0.5
+            c.state = State.STUCK
+            if c.stuck_counter >= MAX_STUCK_FOR_RETIREMENT:
+                c.state = State.RETIRED
+            c.u_k = (np.random.rand(Mr) + 1j * np.random.rand(Mr)) / np.sqrt(Mr)
+            c.right_v_k = (np.random.rand(Mc) + 1j * np.random.rand(Mc)) / np.sqrt(Mc)
+            c.sigma_k = 1.0
+            redo.append(c)
+    if redo:
+        r = engine.svd_residual(np.stack([c.u_k for c in redo]), np.stack([c.right_v_k for c in redo]),
+                                [float(c.sigma_k) for c in redo])
+        for c, ri in zip(redo, r):
+            c.residual_k = np.float64(ri)
+    for c in cands:
         c.param_history.append(c.get_current_solution_params())                                # AMS:303-304
         c.residual_history.append(c.residual_k)
         _adapt_and_test(c, State, conv_tol)

@@ -141,6 +141,18 @@ int maus_step(maus_ctx* ctx, int64_t C, int problem_type, int method, double* V_
               const double* psi, const uint64_t* rng_key, const uint8_t* use_jacobi, int res_slot,
               double* lambda_out, double* resid_out, double* mixnorm_out, int32_t* status_out, int32_t* iters_out);
 
+/* ---- SVD power-sweep branch (AMS:227-255 sweep, AMS:300-301 residual) ----------------------- */
+/* rectangular rows x cols complex128 matrix, row-major (the SVD problem matrix of AMS:343) */
+int maus_svd_set_matrix(maus_ctx* ctx, int64_t rows, int64_t cols, const double* A_rowmajor);
+/* one sweep for C candidates: u <- A v / ||A v||, v <- A^H u / ||A^H u||, sigma = max of the two norms, residual =
+ * ||A v - sigma u|| + ||A^H u - sigma v||.  U_io [C][rows], V_io [C][cols] are updated in place.
+ * status: V_COLLAPSED = ||v|| < 1e-10 on entry (AMS:229), MIX_COLLAPSED = ||u|| < 1e-10 after the first half sweep
+ * (AMS:236); such candidates are left for the host's exception branch (AMS:249-255). */
+int maus_svd_step(maus_ctx* ctx, int64_t C, double* U_io, double* V_io, double* sigma_out, double* resid_out,
+                  int32_t* status_out);
+/* residual only (AMS:301) for host-replaced (u, v, sigma) */
+int maus_svd_residual(maus_ctx* ctx, int64_t C, const double* U, const double* V, const double* sigma, double* resid_out);
+
 /* debug / parity: C = beta*C + s*A*B on column-major complex128 host matrices (A: M x K, B: K x N, C: M x N,
  * `batch` of each, densely packed) through the tensor-pipe kernel (use_dmma != 0) or the plain FP64-FMA kernel. */
 int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, const double* A, const double* B, double* C,
