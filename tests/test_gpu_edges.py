@@ -177,3 +177,32 @@ def test_full_size_properties_k3(eng):
         assert abs(out["lam"][c] - mo.rayleigh_quotient(A, V0[c])) <= 1e-12
         r = np.linalg.norm(A @ V[c] - out["lam"][c] * V[c])
         assert abs(out["resid"][c] - r) <= 1e-11 * r + 1e-13
+
+
+def test_philox_skip_is_bit_exact():
+    """lu_build_aug skips the Philox draw where it provably cannot change a bit; the result must be identical to always
+    drawing (MAUS_PHILOX_ALWAYS=1), including near-converged shifts where diagonal entries of A - sigma I are tiny."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import adaptive_matrix_solver_b200 as pkg
+from adaptive_matrix_solver_b200.workloads import k2_matrix
+n, C = 200, 6
+A = k2_matrix(n, seed=5)
+ev = np.linalg.eigvals(A)
+rng = np.random.default_rng(0)
+RHS = rng.standard_normal((C, n)) + 1j * rng.standard_normal((C, n))
+sig = np.concatenate([ev[:3] * (1 + 1e-13), np.diag(A)[:3]])      # near-singular shifts and exact diagonal cancellations
+psi = np.array([1e-20, 1e-18, 1e-15, 1e-20, 1e-12, 1e-6])
+e = pkg.MausEngine(0); e.set_matrix(A)
+X, st, _ = e.solve_shifted(sig, psi, rng_key=np.arange(C) + 77, RHS=RHS)
+sys.stdout.buffer.write(X.tobytes())
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, MAUS_PHILOX_ALWAYS=flag)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, check=True).stdout)
+    assert len(outs[0]) == 200 * 6 * 16 and outs[0] == outs[1]
