@@ -12,7 +12,8 @@ It performs, for every live EIGENVALUE (non-Hermitian) / SOLVE_LINEAR_SYSTEM can
 the reference mutates, so ``_update_global_diagnostics`` / ``_adjust_global_strategy`` / ``_manage_candidates`` run
 unmodified afterwards.  All numerics (Rayleigh quotient, shifted solve, mix, normalise, residual) run in ONE fused
 CUDA call for the whole population; only the rare failures walk the Psi ladder (AMS:43-104) through the granular
-calls.  Hermitian-eigen and SVD candidates are passed to the reference method untouched.
+calls.  SVD candidates run the batched power sweep of ``svd.cu``; Hermitian-eigen candidates are
+passed to the reference method untouched.
 
 Deliberate deviations (DESIGN.md section "Deviations"): the dense Psi perturbation (AMS:49) comes from a
 counter-based device RNG, not from the global numpy stream; host RNG draws therefore happen only for the
