@@ -107,6 +107,9 @@ def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, e
     live = [c for c in candidates if c.state not in (State.CONVERGED, State.RETIRED)]
     if not live:
         return 0
+    if live[0].problem_type.value not in (_abi.EIGENVALUE, _abi.SOLVE_LINEAR_SYSTEM):
+        # SVD / other branches: not sharded (every rank steps its own replica of the whole population)
+        return step_population(candidates, M, b, strat_params, problem_knowledge, engine)
     n = live[0].N_diag
     eigen = live[0].problem_type.value == _abi.EIGENVALUE
     counts = [len(range(r, len(live), shard.world)) for r in range(shard.world)]
