@@ -3,15 +3,17 @@
 // Right-looking blocked LU on AUGMENTED systems W_b = [H_b | rhs_b] (column-major, ld = n, n+1 columns): the
 // right-hand side rides along as column n, so after the last step it holds y = L^-1 P rhs and only the
 // back-substitution with U remains; L is never needed again, which is why the row permutation is applied to the
-// columns at and right of the panel only.
+// columns at and right of the current outer block only.  The schedule (two-level blocking: 4 panels per outer block,
+// bulk trailing update with K = 512) lives in maus_lu_solve (maus_api.cu); the kernels of one panel step are:
 //
-// Per outer step (panel width 128):
+// Per panel (width 128):
 //   lu_panel        one thread-block CLUSTER per candidate (up to 8 CTAs x 512 threads); every thread owns one or
 //                   two rows of the panel and keeps a 16 (8) column inner block of them in registers.  Pivot search
 //                   (BLAS izamax metric |re|+|im|, first maximum) = warp shuffle -> CTA -> cluster reduction through
 //                   distributed shared memory, one cluster barrier per column.  Pivoting is IMPLICIT inside the
 //                   panel (rows are marked, not moved); the net permutation is emitted as <= 256 (dst, src) pairs.
-//   lu_permute_rows applies those pairs to every column >= k0 in one parallel pass (no sequential swap chain).
+//   lu_permute_rows applies those pairs to every column >= the outer block's first column in one parallel pass (no
+//                   sequential swap chain).
 //   lu_trtri        inverse of the unit-lower 128 x 128 diagonal block, so that the triangular solve for U12 and the
 //                   trailing update are both plain GEMMs on the FP64 tensor pipe (zgemm.cu).
 #include <cooperative_groups.h>
