@@ -4,6 +4,7 @@
 #include <cstring>
 #include <new>
 #include <algorithm>
+#include <functional>
 #include "ctx.cuh"
 #include "vec.cuh"
 #include "spmv.cuh"
@@ -495,6 +496,8 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
         };
         static int lu_group = 0;
         if (!lu_group) { const char* e = getenv("MAUS_LU_GROUP"); lu_group = e ? std::max(1, atoi(e)) : 4; }
+        static int lu_leaf = 0;      // width of the panels the cluster kernel factors (multiple of 8, <= 128)
+        if (!lu_leaf) { const char* e = getenv("MAUS_LU_LEAF"); lu_leaf = e ? std::min(LU_NB, std::max(8, atoi(e))) : 64; }
         for (int k0 = 0; k0 < n; k0 += lu_group * LU_NB) {
             const int kend = std::min(n, k0 + lu_group * LU_NB);       // end of the outer block
             const int nc_out = n + 1 - kend;                           // columns right of the outer block (incl. rhs)
@@ -502,7 +505,19 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
                 const int jb = std::min(LU_NB, kend - kp);
                 // the panel's columns are up to date (updates (a) of the previous panels of this block);
                 // its permutation also reorders the L columns k0..kp of the block, whose trailing update is pending
-                MAUS_CUDA(ctx, factor_panel(kp, jb, k0));
+                // the 128-wide panel is factored recursively from `lu_leaf`-wide leaves (less in-panel update work and
+                // traffic): left half, U = L11^-1 * (its rows, columns of the right half), rank-w/2 update of the right
+                // half's columns, right half.  All permutations reach back to the outer block's first column.
+                std::function<int(int, int)> factor_block = [&](int kb, int w) -> int {
+                    if (w <= lu_leaf) { MAUS_CUDA(ctx, factor_panel(kb, w, k0)); return MAUS_OK; }
+                    const int wl = ((w / 2 + lu_leaf - 1) / lu_leaf) * lu_leaf, wr = w - wl, km = kb + wl;
+                    int r1 = factor_block(kb, wl); if (r1) return r1;
+                    MAUS_CUDA(ctx, solve_u12(kb, wl, wr));
+                    if (n - km > 0)
+                        MAUS_CUDA(ctx, gemm(W_at(km, kb), n, strideW, W_at(kb, km), W_at(km, km), n - km, wr, wl, 1, 1));
+                    return factor_block(km, wr);
+                };
+                { int r0 = factor_block(kp, jb); if (r0) return r0; }
                 const int kq = kp + jb;
                 // (b) this row block, columns right of the outer block: pending updates of the block's earlier panels
                 if (kp > k0 && nc_out > 0)

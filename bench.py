@@ -79,7 +79,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def lu_gemm_algorithmic(n, cand, nb=128, group=4):
+def lu_gemm_algorithmic(n, cand, nb=128, group=4, leaf=64):
     """(launches, flops, bytes) of the GEMM launches of ONE batched LU generation, following the schedule of
     maus_lu_solve (csrc/maus_api.cu): per launch bytes = C read (beta = 1) + C write + A + B, complex128."""
     launches, flops, byts = 0, 0.0, 0.0
@@ -98,6 +98,18 @@ def lu_gemm_algorithmic(n, cand, nb=128, group=4):
         kp = k0
         while kp < kend:
             jb = min(nb, kend - kp)
+
+            def block(kb, w):                      # recursive halving of the panel down to `leaf`-wide cluster panels
+                if w <= leaf:
+                    return
+                wl = ((w // 2 + leaf - 1) // leaf) * leaf
+                wr, km = w - wl, kb + wl
+                block(kb, wl)
+                g(wl, wr, wl, 0)
+                if n - km > 0:
+                    g(n - km, wr, wl, 1)
+                block(km, wr)
+            block(kp, jb)
             kq = kp + jb
             if kp > k0 and nc_out > 0:
                 g(jb, nc_out, kp - k0, 1)
