@@ -123,9 +123,9 @@ def lu_gemm_algorithmic(n, cand, nb=128, group=4, leaf=64):
     return launches, flops, byts
 
 
-# DRAM traffic of the LU GEMM launches measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum over the 87 launches
-# of one generation at n = 4096 with 16 candidates: profiles/gemm_traffic_r01_c16.csv), per candidate
-NCU_GEMM_DRAM_BYTES_PER_CANDIDATE = (31.32e9 + 12.98e9) / 16.0
+# DRAM traffic of the GEMM launches measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum over the 151 LU launches
+# + 2 batched A*V launches of one generation at n = 4096 with 16 candidates: profiles/launches_r01_final.csv), per candidate
+NCU_GEMM_DRAM_BYTES_PER_CANDIDATE = (33.565e9 + 13.110e9) / 16.0
 
 
 def vector_alpha_update(alpha, resid, prev):
@@ -247,7 +247,7 @@ def run_b200(args):
                 "frac": round(achieved / FP64_PEAK_TFLOPS, 4),
                 "traffic": round(NCU_GEMM_DRAM_BYTES_PER_CANDIDATE * C_ / per_launch) if n == 4096 else None,
                 "traffic_unit": "bytes per launch (ncu dram read+write, average over the LU GEMM launches of a generation; "
-                                "measured at 16 candidates and scaled by the candidate count, profiles/gemm_traffic_r01_c16.csv)",
+                                "measured at 16 candidates and scaled by the candidate count, profiles/launches_r01_final.csv)",
                 "algorithmic_flops_per_launch": round(alg_flops / n_launch), "algorithmic_bytes_per_launch": round(alg_bytes / n_launch),
                 "peak_source": "own measurement (FP64 DMMA, profiles/fp64_peak_r01.txt); MEASURED_PEAKS.json has no FP64 entry",
                 "share_of_step": round(gemm_s / (dev_ms / 1e3), 4) if dev_ms > 0 else None,
