@@ -93,13 +93,22 @@ if "k5" in sections:
     rng = np.random.default_rng(1)
     V = rng.random((C_, n)) + 1j * rng.random((C_, n)); V /= np.linalg.norm(V, axis=1, keepdims=True)
     eng.upload_vectors(V)
+    import scipy.sparse as sp
+    # (a) linear system A x = b (sigma = 0): the diagonally dominant operator GMRES(20) solves in about one cycle
+    t0 = time.perf_counter()
+    X, st, it = eng.solve_shifted(np.zeros(C_, dtype=complex), np.full(C_, 5e-19), rng_key=None, method=_abi.METHOD_GMRES, RHS=None)
+    dt = time.perf_counter() - t0
+    rel = float(np.linalg.norm(A @ X[0] - V[0]) / np.linalg.norm(V[0]))
+    emit(config="K5 sparse n=1M nnz/row~21 c8 GMRES(20), linear system (sigma = 0)", seconds=round(dt, 4), status=st.tolist(),
+         inner_iters=it.tolist(), rel_residual_c0=rel, ms_per_candidate_solve=round(dt / C_ * 1e3, 2))
+    # (b) eigen step: shift = Rayleigh quotient of a random vector lies INSIDE the spectrum -> GMRES(20) x 50 stagnates, exactly
+    # like scipy on the same operator (parity-tested at n = 3000); the reference's ladder then falls back
     lam, _ = eng.rq(C_=C_)
     t0 = time.perf_counter()
     X, st, it = eng.solve_shifted(lam, np.full(C_, 5e-19), rng_key=None, method=_abi.METHOD_GMRES, RHS=None)
     dt = time.perf_counter() - t0
-    c = 0
-    H = A - lam[c] * __import__("scipy.sparse", fromlist=["eye"]).eye(n, format="csc")
-    rel = float(np.linalg.norm(H @ X[c] - V[c]) / np.linalg.norm(V[c]))
-    emit(config="K5 sparse n=1M nnz/row~21 c8 GMRES(20)", seconds=round(dt, 3), status=st.tolist(), inner_iters=it.tolist(),
-         rel_residual_c0=rel, ms_per_candidate_solve=round(dt / C_ * 1e3, 2))
+    H = A - lam[0] * sp.eye(n, format="csc")
+    rel = float(np.linalg.norm(H @ X[0] - V[0]) / np.linalg.norm(V[0]))
+    emit(config="K5 sparse n=1M c8 GMRES(20)x50, eigen shift inside the spectrum", seconds=round(dt, 3), status=st.tolist(),
+         inner_iters=it.tolist(), rel_residual_c0=rel, ms_per_inner_iteration_all_candidates=round(dt / max(1, int(it.max())) * 1e3, 3))
 eng.close()
