@@ -63,6 +63,8 @@ struct maus_ctx {
     void* gmres = nullptr;
     // SVD branch (svd.cu): rectangular matrix in four layouts + candidate buffers
     void* svd = nullptr;
+    // row-sharded sparse operator + NCCL communicator (rowshard.cu)
+    void* rowshard = nullptr;
 
     long long launches = 0;
     long long bytes_held = 0;
@@ -97,3 +99,4 @@ int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double
                      int* iters, double max_psi_host);
 void maus_gmres_free(maus_ctx* ctx);
 void maus_svd_free(maus_ctx* ctx);
+void maus_rowshard_free(maus_ctx* ctx);

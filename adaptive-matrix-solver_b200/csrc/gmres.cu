@@ -16,7 +16,9 @@
 #include <vector>
 #include <algorithm>
 #include <cfloat>
+#include <functional>
 #include "ctx.cuh"
+#include "gmres.cuh"
 
 namespace {
 
@@ -50,12 +52,13 @@ struct GmresCand {
 
 struct GmresWs {
     long long n = 0, C = 0;
-    int m = 0, nblk = 0;
+    int m = 0, m_cap = 0, nblk = 0;
     cplx *Vk = nullptr, *w = nullptr, *z = nullptr, *x = nullptr, *r = nullptr, *minv = nullptr;
     cplx* partial = nullptr;      // [C][GM_MAXBLK]
     GmresCand* cand = nullptr;
     int* counters = nullptr;      // [0] = inner_active count, [1] = active count
     int* jacbad = nullptr;        // [C]
+    cplx* red = nullptr;          // [C] compact reduction record (row-sharded mode)
     size_t bytes = 0;
 };
 
@@ -80,11 +83,25 @@ __device__ __forceinline__ void chunk_range(long long n, int nblk, int blk, long
     i1 = i0 + per < n ? i0 + per : n;
 }
 
+// row-sharded mode: every rank holds a slice of each vector, so a partial-sum record must be summed over the ranks before
+// it is consumed.  collapse -> red[b] (compact, all-reduced by NCCL) -> expand back into slot 0 of the record.
+__global__ void gm_collapse_kernel(const cplx* __restrict__ partial, cplx* __restrict__ red, int C, int nblk) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < C) red[b] = sum_partials(partial, b, nblk);
+}
+__global__ void gm_expand_kernel(cplx* __restrict__ partial, const cplx* __restrict__ red, int C, int nblk) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= C) return;
+    partial[b * GM_MAXBLK] = red[b];
+    for (int q = 1; q < nblk; ++q) partial[b * GM_MAXBLK + q] = cmake(0.0, 0.0);
+}
+
 // ---- setup ------------------------------------------------------------------------------------------------------
 // Jacobi: d_i = A_ii - sigma + psi (+ R_ii);  minv = 1/d when requested; validity (all finite, |d| > 1e-12) -> jacbad
 __global__ void gm_precond_kernel(const cplx* __restrict__ diagA, long long n, const cplx* __restrict__ sigma,
                                   const double* __restrict__ psi, const unsigned long long* __restrict__ keys,
-                                  const unsigned char* __restrict__ jac, cplx* __restrict__ minv, int* jacbad, int nblk) {
+                                  const unsigned char* __restrict__ jac, cplx* __restrict__ minv, int* jacbad, int nblk,
+                                  long long row0) {
     const int b = blockIdx.y;
     long long i0, i1; chunk_range(n, nblk, blockIdx.x, i0, i1);
     const bool want = jac && jac[b];
@@ -95,7 +112,7 @@ __global__ void gm_precond_kernel(const cplx* __restrict__ diagA, long long n, c
             cplx d = diagA[i];
             d.x -= sigma[b].x; d.y -= sigma[b].y;           // T = A - sigma I (AMS:270)
             cplx reg = cmake(psi[b], 0.0);                    // + psi I (+ R_ii), AMS:47-52
-            if (keys) { cplx r = psi_perturbation(keys[b], (uint32_t)i, (uint32_t)i, psi[b]); reg.x += r.x; reg.y += r.y; }
+            if (keys) { cplx r = psi_perturbation(keys[b], (uint32_t)(row0 + i), (uint32_t)(row0 + i), psi[b]); reg.x += r.x; reg.y += r.y; }
             d.x += reg.x; d.y += reg.y;
             mi = crecip(d);                                   // AMS:70
             const double ad = hypot(d.x, d.y);
@@ -455,20 +472,19 @@ void maus_gmres_free(maus_ctx* ctx) {
     GmresWs* ws = (GmresWs*)ctx->gmres;
     if (!ws) return;
     cudaFree(ws->Vk); cudaFree(ws->w); cudaFree(ws->z); cudaFree(ws->x); cudaFree(ws->r); cudaFree(ws->minv);
-    cudaFree(ws->partial); cudaFree(ws->cand); cudaFree(ws->counters); cudaFree(ws->jacbad);
+    cudaFree(ws->partial); cudaFree(ws->cand); cudaFree(ws->counters); cudaFree(ws->jacbad); cudaFree(ws->red);
     ctx->bytes_held -= (long long)ws->bytes;
     delete ws;
     ctx->gmres = nullptr;
 }
 
-static int gmres_ensure(maus_ctx* ctx, long long C, GmresWs** out) {
+static int gmres_ensure(maus_ctx* ctx, long long n, long long C, GmresWs** out) {
     GmresWs* ws = (GmresWs*)ctx->gmres;
-    const long long n = ctx->n;
     if (ws && ws->n == n && ws->C >= C) { *out = ws; return MAUS_OK; }
     if (ws) { MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); maus_gmres_free(ctx); }
     ws = new GmresWs();
     ws->n = n; ws->C = std::max<long long>(C, 4);
-    ws->m = (int)std::min<long long>(GM_RESTART, n);
+    ws->m = ws->m_cap = GM_RESTART;          // Krylov slots are sized for the full restart length
     ws->nblk = (int)std::max<long long>(1, std::min<long long>(GM_MAXBLK, (n + 4 * GM_NT - 1) / (4 * GM_NT)));
     const size_t vec = (size_t)ws->C * n * sizeof(cplx);
     cudaError_t e;
@@ -480,6 +496,7 @@ static int gmres_ensure(maus_ctx* ctx, long long C, GmresWs** out) {
     GM_ALLOC(ws->cand, (size_t)ws->C * sizeof(GmresCand));
     GM_ALLOC(ws->counters, 2 * sizeof(int));
     GM_ALLOC(ws->jacbad, (size_t)ws->C * sizeof(int));
+    GM_ALLOC(ws->red, (size_t)ws->C * sizeof(cplx));
 #undef GM_ALLOC
     ws->bytes = total;
     ctx->bytes_held += (long long)total;
@@ -488,32 +505,45 @@ static int gmres_ensure(maus_ctx* ctx, long long C, GmresWs** out) {
     return MAUS_OK;
 }
 
-int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* psi, const unsigned long long* keys,
-                     const unsigned char* use_jacobi, const cplx* rhs, long long rhs_stride, cplx* X, int* status,
-                     int* iters, double max_psi_host) {
+// The solver proper, written against GmresOperator (gmres.cuh): `n` is the LOCAL vector length, op.matvec applies the
+// shared matrix to C vectors, op.reduce_sync / op.flag_sync make partial sums / flags global in row-sharded mode.
+int gmres_core(maus_ctx* ctx, const GmresOperator& op, long long C, const cplx* sigma, const double* psi,
+               const unsigned long long* keys, const unsigned char* use_jacobi, const cplx* rhs, long long rhs_stride, cplx* X,
+               int* status, int* iters, double max_psi_host) {
     GmresWs* ws = nullptr;
-    int rc = gmres_ensure(ctx, C, &ws); if (rc) return rc;
-    MatrixSlot& s = ctx->slot[0];
-    const long long n = ctx->n;
+    const long long n = op.nloc;
+    int rc = gmres_ensure(ctx, n, C, &ws); if (rc) return rc;
+    // restart = min(20, GLOBAL order) (scipy), not the local slice length
+    ws->m = (int)std::min<long long>(GM_RESTART, std::min<long long>(op.nglobal, ws->m_cap));
     const int m = ws->m, nblk = ws->nblk;
     cudaStream_t st = ctx->stream;
     const dim3 gridv(nblk, (unsigned)C), gridc((unsigned)((C + 127) / 128));
-    const bool dense = s.dense && !s.sparse;
-    if (s.sparse) keys = nullptr;                          // AMS:47: the sparse regulariser has no random part
     // the random perturbation only matters once 0.15*psi exceeds rounding of the matvec (~1e-17 * max|a_ij|)
-    const double gate = 1e-17 * std::max(s.amax, 1e-300);
-    const bool any_perturb = dense && keys && (0.15 * max_psi_host > gate);
+    const double gate = 1e-17 * std::max(op.amax, 1e-300);
+    const bool any_perturb = op.dense && keys && (0.15 * max_psi_host > gate);
     int host_counters[2];
+    auto sync_partials = [&]() -> int {
+        if (!op.reduce_sync) return MAUS_OK;
+        gm_collapse_kernel<<<gridc, 128, 0, st>>>(ws->partial, ws->red, (int)C, nblk);
+        int r2 = op.reduce_sync(ws->red, C);
+        if (r2) return r2;
+        gm_expand_kernel<<<gridc, 128, 0, st>>>(ws->partial, ws->red, (int)C, nblk);
+        ctx->launches += 2;
+        return MAUS_OK;
+    };
+#define GM_SYNC() do { if ((rc = sync_partials())) return rc; } while (0)
 
     MAUS_CUDA(ctx, cudaMemsetAsync(ws->jacbad, 0, (size_t)C * sizeof(int), st));
-    gm_precond_kernel<<<gridv, GM_NT, 0, st>>>(s.diag, n, sigma, psi, keys, use_jacobi, ws->minv, ws->jacbad, nblk);
+    gm_precond_kernel<<<gridv, GM_NT, 0, st>>>(op.diag, n, sigma, psi, keys, use_jacobi, ws->minv, ws->jacbad, nblk, op.row0);
+    if (op.flag_sync && (rc = op.flag_sync(ws->jacbad, C))) return rc;
     gm_init_kernel<<<gridc, 128, 0, st>>>(ws->cand, sigma, psi, use_jacobi, ws->jacbad, status, (int)C, gate, keys != nullptr);
     gm_norms_b_kernel<<<gridv, GM_NT, 0, st>>>(rhs, rhs_stride, ws->minv, ws->cand, n, ws->x, ws->partial, nblk);
+    GM_SYNC();
     gm_after_norms_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk);
     ctx->launches += 4;
 
     auto matvec = [&](const cplx* v, long long ldv) -> int {
-        int r2 = maus_apply_matrix(ctx, 0, v, ldv, ws->z, n, C);
+        int r2 = op.matvec(v, ldv, ws->z, n, C);
         if (r2) return r2;
         if (any_perturb) {
             // launched only if some candidate's psi puts R above rounding; per-candidate test inside the kernel
@@ -528,6 +558,7 @@ int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double
     // r = b - H x0 ; pre-loop convergence test
     if ((rc = matvec(ws->x, n))) return rc;
     gm_residual_kernel<<<gridv, GM_NT, 0, st>>>(rhs, rhs_stride, ws->z, ws->x, ws->cand, n, ws->r, ws->partial, nblk);
+    GM_SYNC();
     MAUS_CUDA(ctx, cudaMemsetAsync(ws->counters, 0, 2 * sizeof(int), st));
     gm_cycle_end_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, 1, 0, ws->counters);
     ctx->launches += 2;
@@ -538,18 +569,22 @@ int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double
     for (int outer = 0; outer < GM_MAXITER && n_active > 0; ++outer) {
         MAUS_CUDA(ctx, cudaMemsetAsync(ws->counters, 0, 2 * sizeof(int), st));
         gm_start_kernel<<<gridv, GM_NT, 0, st>>>(ws->r, ws->minv, ws->cand, n, ws->w, ws->partial, nblk);
+        GM_SYNC();
         gm_start_scalar_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, ws->counters);
         gm_store_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->cand, n, m, ws->Vk, 0, nblk, 1);
         ctx->launches += 3;
         for (int col = 0; col < m; ++col) {
             if ((rc = matvec(ws->Vk + (long long)col * n, (long long)(m + 1) * n))) return rc;
             gm_post_matvec_kernel<<<gridv, GM_NT, 0, st>>>(ws->z, ws->Vk, ws->minv, ws->cand, n, m, col, ws->w, ws->partial, nblk);
+            GM_SYNC();
             gm_h0_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk);
             for (int k = 0; k <= col; ++k) {
                 gm_mgs_pass_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->Vk, ws->cand, n, m, k, 0, ws->partial, nblk);
+                GM_SYNC();
                 gm_mgs_scalar_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, k);
             }
             gm_mgs_pass_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->Vk, ws->cand, n, m, col + 1, 1, ws->partial, nblk);
+            GM_SYNC();
             MAUS_CUDA(ctx, cudaMemsetAsync(ws->counters, 0, sizeof(int), st));
             gm_hess_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, m, ws->counters);
             gm_store_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->cand, n, m, ws->Vk, 1, nblk, 1);
@@ -563,6 +598,7 @@ int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double
         gm_update_x_kernel<<<gridv, GM_NT, 0, st>>>(ws->x, ws->Vk, ws->cand, n, m, nblk);
         if ((rc = matvec(ws->x, n))) return rc;
         gm_residual_kernel<<<gridv, GM_NT, 0, st>>>(rhs, rhs_stride, ws->z, ws->x, ws->cand, n, ws->r, ws->partial, nblk);
+        GM_SYNC();
         MAUS_CUDA(ctx, cudaMemsetAsync(ws->counters, 0, 2 * sizeof(int), st));
         gm_cycle_end_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, 0, outer == GM_MAXITER - 1, ws->counters);
         ctx->launches += 4;
@@ -572,6 +608,24 @@ int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double
     }
     gm_finish_kernel<<<gridv, GM_NT, 0, st>>>(ws->cand, ws->x, n, X, status, iters, nblk);
     ctx->launches += 1;
+    if (op.flag_sync) {
+        // a non-finite entry on ANY rank's slice fails the candidate everywhere (AMS:94-95)
+        if ((rc = op.flag_sync(status, C))) return rc;
+    }
     MAUS_CUDA(ctx, cudaGetLastError());
     return MAUS_OK;
+#undef GM_SYNC
+}
+
+// replicated matrix on one GPU (the default path)
+int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* psi, const unsigned long long* keys,
+                     const unsigned char* use_jacobi, const cplx* rhs, long long rhs_stride, cplx* X, int* status,
+                     int* iters, double max_psi_host) {
+    MatrixSlot& s = ctx->slot[0];
+    GmresOperator op;
+    op.nloc = ctx->n; op.nglobal = ctx->n; op.row0 = 0;
+    op.diag = s.diag; op.amax = s.amax; op.dense = s.dense && !s.sparse;
+    op.matvec = [ctx](const cplx* v, long long ldv, cplx* z, long long ldz, long long Cn) { return maus_apply_matrix(ctx, 0, v, ldv, z, ldz, Cn); };
+    if (s.sparse) keys = nullptr;                          // AMS:47: the sparse regulariser has no random part
+    return gmres_core(ctx, op, C, sigma, psi, keys, use_jacobi, rhs, rhs_stride, X, status, iters, max_psi_host);
 }

@@ -177,6 +177,7 @@ extern "C" int maus_destroy(maus_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     reset_for_n(ctx, 0);
     maus_svd_free(ctx);
+    maus_rowshard_free(ctx);
     for (auto& e : ctx->prof.ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

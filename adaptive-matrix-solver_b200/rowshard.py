@@ -1,0 +1,130 @@
+"""Row-sharded sparse operator: BASELINE config #5 as worded ("sparse CSC ... row-sharded across 8 B200").
+
+Rank r owns rows [r*n/G, (r+1)*n/G) of A (a CSR slice with global column indices) and the same slice of every candidate
+vector.  The library all-gathers the input of each SpMM over NVLink and all-reduces every GMRES dot product (NCCL, bound
+at run time inside libmaus_b200: ``maus_dist_init``).  The solver is the SAME batched GMRES as the replicated path
+(AMS:61-90 -> scipy gmres control flow); only the operator differs.  One process per GPU; the 128-byte NCCL id travels
+through ``torch.distributed`` (any backend) or a caller-supplied broadcast.
+"""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+
+from ._abi import MausError
+
+_c128 = np.complex128
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def nccl_library_path():
+    """libnccl.so.2 that torch itself loads (so that both users share one copy); '' = let the loader search"""
+    try:
+        import nvidia.nccl
+        base = list(getattr(nvidia.nccl, "__path__", [])) or [os.path.dirname(nvidia.nccl.__file__)]
+        for b in base:
+            hits = sorted(glob.glob(os.path.join(b, "lib", "libnccl.so*")))
+            if hits:
+                return hits[0]
+    except Exception:
+        pass
+    return ""
+
+
+def row_block(n, rank, world):
+    """(row0, nrows) of the block a rank owns; equal blocks are required (the all-gather is not ragged)"""
+    if n % world:
+        raise ValueError(f"row sharding needs n % world == 0 (n={n}, world={world}); pad the operator")
+    nloc = n // world
+    return rank * nloc, nloc
+
+
+def csr_row_block(A, rank, world):
+    """CSR slice (rowptr[nloc+1] rebased to 0, global colidx, values) of a scipy.sparse matrix for one rank"""
+    Ar = A.tocsr()
+    Ar.sort_indices()
+    n = Ar.shape[0]
+    if Ar.shape[0] != Ar.shape[1]:
+        raise ValueError("square matrix required")
+    row0, nloc = row_block(n, rank, world)
+    lo, hi = int(Ar.indptr[row0]), int(Ar.indptr[row0 + nloc])
+    rowptr = np.ascontiguousarray(Ar.indptr[row0:row0 + nloc + 1], dtype=np.int64) - lo
+    colidx = np.ascontiguousarray(Ar.indices[lo:hi], dtype=np.int64)
+    vals = np.ascontiguousarray(Ar.data[lo:hi], dtype=_c128)
+    return n, row0, nloc, rowptr, colidx, vals
+
+
+class RowShardedOperator:
+    """One rank's part of the row-sharded operator, living in ``engine``'s context."""
+
+    def __init__(self, engine, rank=0, world=1, broadcast=None):
+        """``broadcast(bytes_or_None) -> bytes``: returns rank 0's argument on every rank.  Default: torch.distributed
+        (``broadcast_object_list``) when world > 1."""
+        self.engine, self.rank, self.world = engine, int(rank), int(world)
+        self._lib = engine._lib
+        lib = nccl_library_path().encode()
+        ident = None
+        if self.rank == 0:
+            buf = C.create_string_buffer(128)
+            rc = self._lib.maus_nccl_unique_id(lib, buf)
+            if rc != 0:
+                raise MausError(f"maus_nccl_unique_id failed (rc={rc}): libnccl.so.2 not loadable")
+            ident = buf.raw
+        if self.world > 1:
+            if broadcast is None:
+                import torch.distributed as dist
+                box = [ident]
+                dist.broadcast_object_list(box, src=0)
+                ident = box[0]
+            else:
+                ident = broadcast(ident)
+        engine._check(self._lib.maus_dist_init(engine._h, lib, self.rank, self.world, ident))
+        self.n = self.row0 = self.nloc = 0
+
+    def set_matrix(self, A):
+        """A: the FULL scipy.sparse matrix (every rank slices its own rows) -- or use ``set_row_block`` directly"""
+        return self.set_row_block(*csr_row_block(A, self.rank, self.world))
+
+    def set_row_block(self, n, row0, nloc, rowptr, colidx, vals):
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        colidx = np.ascontiguousarray(colidx, dtype=np.int64)
+        vals = np.ascontiguousarray(vals, dtype=_c128)
+        self.engine._check(self._lib.maus_set_csr_rowblock(self.engine._h, int(n), int(row0), int(nloc),
+                                                           _ip(rowptr, C.c_int64), _ip(colidx, C.c_int64), _dp(vals)))
+        self.n, self.row0, self.nloc = int(n), int(row0), int(nloc)
+
+    def local(self, full):
+        """slice [..., row0:row0+nloc] of full-length vector(s)"""
+        return np.ascontiguousarray(np.asarray(full)[..., self.row0:self.row0 + self.nloc], dtype=_c128)
+
+    def matvec(self, V_local):
+        V_local = np.ascontiguousarray(V_local, dtype=_c128)
+        if V_local.ndim != 2 or V_local.shape[1] != self.nloc:
+            raise ValueError("V_local must be [C][nloc]")
+        Y = np.empty_like(V_local)
+        self.engine._check(self._lib.maus_rs_matvec(self.engine._h, V_local.shape[0], _dp(V_local), _dp(Y)))
+        return Y
+
+    def gmres(self, sigma, psi, RHS_local, use_jacobi=None, want_x=True):
+        """x_c = (A - sigma_c I + psi_c I)^-1 rhs_c; returns (X_local [C][nloc], status [C], inner iterations [C])"""
+        sigma = np.ascontiguousarray(np.atleast_1d(sigma), dtype=_c128)
+        C_ = sigma.shape[0]
+        psi = np.ascontiguousarray(np.atleast_1d(psi), dtype=np.float64)
+        RHS_local = np.ascontiguousarray(RHS_local, dtype=_c128)
+        if RHS_local.shape != (C_, self.nloc) or psi.shape != (C_,):
+            raise ValueError("sigma [C], psi [C], RHS_local [C][nloc] expected")
+        jac = None if use_jacobi is None else np.ascontiguousarray(np.atleast_1d(use_jacobi), dtype=np.uint8)
+        X = np.empty((C_, self.nloc), dtype=_c128) if want_x else None
+        status = np.empty(C_, dtype=np.int32)
+        iters = np.empty(C_, dtype=np.int32)
+        self.engine._check(self._lib.maus_rs_gmres(self.engine._h, C_, _dp(sigma), _dp(psi), _ip(jac, C.c_uint8),
+                                                   _dp(RHS_local), _dp(X), _ip(status, C.c_int32), _ip(iters, C.c_int32)))
+        return X, status, iters

@@ -153,6 +153,23 @@ int maus_svd_step(maus_ctx* ctx, int64_t C, double* U_io, double* V_io, double* 
 /* residual only (AMS:301) for host-replaced (u, v, sigma) */
 int maus_svd_residual(maus_ctx* ctx, int64_t C, const double* U, const double* V, const double* sigma, double* resid_out);
 
+/* ---- row-sharded sparse operator (BASELINE config 5 as worded) ---------------------------------- */
+/* Every rank owns n / world consecutive rows of A and the same slice of every vector; a matvec all-gathers its input,
+ * GMRES all-reduces its dot products (NCCL over NVLink, bound at run time from `libpath` = the libnccl.so.2 the process
+ * already uses, e.g. torch's).  rank 0 creates the id, the host layer broadcasts the 128 bytes. */
+int maus_nccl_unique_id(const char* libpath, char* out128);
+int maus_dist_init(maus_ctx* ctx, const char* libpath, int rank, int world, const char* id128);
+/* CSR slice of rows [row0, row0 + nrows): rowptr has nrows + 1 entries (any base), colidx are GLOBAL column indices;
+ * rowptr / colidx / vals point at the START of the full arrays' slice, i.e. rowptr[i] indexes colidx / vals directly */
+int maus_set_csr_rowblock(maus_ctx* ctx, int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr,
+                          const int64_t* colidx, const double* vals);
+/* Y_local[c] = (A V[c])(local rows); V_local, Y_local: [C][nrows] */
+int maus_rs_matvec(maus_ctx* ctx, int64_t C, const double* V_local, double* Y_local);
+/* x_c = (A - sigma_c I + psi_c I)^-1 rhs_c with the batched GMRES of maus_solve_shifted on the row-sharded operator;
+ * RHS_local / X_local_out are the local slices [C][nrows]; status / iters are identical on every rank */
+int maus_rs_gmres(maus_ctx* ctx, int64_t C, const double* sigma, const double* psi, const uint8_t* use_jacobi,
+                  const double* RHS_local, double* X_local_out, int32_t* status_out, int32_t* iters_out);
+
 /* debug / parity: C = beta*C + s*A*B on column-major complex128 host matrices (A: M x K, B: K x N, C: M x N,
  * `batch` of each, densely packed) through the tensor-pipe kernel (use_dmma != 0) or the plain FP64-FMA kernel. */
 int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, const double* A, const double* B, double* C,
