@@ -439,6 +439,14 @@ static int ensure_lu_workspace(maus_ctx* ctx, long long C, int* batch_out) {
     return MAUS_OK;
 }
 
+// LU trailing updates use the three-real-product complex GEMM (zgemm.cu, 25 % fewer tensor instructions);
+// MAUS_GEMM_3M=0 selects the conventional four-product kernel (A/B measurements, profiles/README_r01.md)
+static int lu_use_3m() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MAUS_GEMM_3M"); v = e ? (atoi(e) != 0) : 1; }
+    return v;
+}
+
 int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* psi, const unsigned long long* keys,
                   const cplx* Rcm, const cplx* rhs, long long rhs_stride, cplx* X, int* status) {
     MatrixSlot& s = ctx->slot[0];
@@ -469,6 +477,7 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
             p.B = B; p.ldb = n; p.strideB = strideW;
             p.C = C; p.ldc = n; p.strideC = strideW;
             p.M = M; p.N = N; p.K = K; p.batch = nb; p.beta = beta; p.negate = negate;
+            p.algo3m = lu_use_3m();
             int h = prof_begin(ctx, MAUS_PROF_LU_GEMM, 8.0 * M * (double)N * K * nb);
             cudaError_t e = zgemm_dmma_launch(p, st);
             prof_end(ctx, h);
@@ -775,6 +784,7 @@ extern "C" int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, c
     p.B = dB; p.ldb = K; p.strideB = (long long)K * N;
     p.C = dC; p.ldc = M; p.strideC = (long long)M * N;
     p.M = M; p.N = N; p.K = K; p.batch = batch; p.beta = beta; p.negate = negate;
+    p.algo3m = (use_dmma == 2) ? 1 : 0;                     // 2: the three-product (3M) tensor-pipe kernel of the LU updates
     cudaError_t e = use_dmma ? zgemm_dmma_launch(p, st) : zgemm_simple_launch(p, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(Cm, dC, bc, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

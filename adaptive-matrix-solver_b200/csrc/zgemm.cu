@@ -258,6 +258,228 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// 3M variant (LU trailing updates).  (Ar + iAi)(Br + iBi) with THREE real products instead of four:
+//   P1 = Ar Br,  P2 = Ai Bi,  P3 = (Ar + Ai)(Br + Bi)      Re = P1 - P2,  Im = P3 - P1 - P2
+// (the "3M" / Karatsuba complex product of ZGEMM3M; normwise as stable as the conventional product, Higham 1992).
+// It executes 6 instead of 8 real flops per complex multiply-add on the same DMMA pipe, i.e. 25 % fewer tensor
+// instructions for the same algorithmic work.  Operands stay interleaved complex in shared memory: one LDS.128 fetches
+// (re, im) of a fragment element, the sums are formed in registers (2 DADD per 18 DMMA).
+//
+//   CTA tile 128 x 48 complex, 8 consumer warps (4 x 2), each 32 x 24 complex = 4 x 3 DMMA tiles x 3 products
+//   (72 f64 accumulators) + 1 producer warp (same TMA bulk-copy rings as above).  Column strides 130 / 36 complex make
+//   the 128-bit fragment loads conflict free per quarter warp.  C is added in the epilogue (accumulators start at 0).
+namespace m3 {
+constexpr int TM = 128, TN = 48;
+constexpr int KC = 16, STAGES = 3;
+constexpr int KCB = 32, BSTAGES = 2;
+constexpr int LDSA = TM + 2, LDSB = KCB + 4;
+constexpr int A_STAGE = KC * LDSA, B_STAGE = TN * LDSB;
+constexpr int QA = 4, QB = 3, NWM = 4, NWN = 2;
+// Register budget: the register file is split per SM sub-partition (16 K registers each), so a 9th warp would cap every
+// thread at 168 registers.  The CTA is launched as three warpgroups (2 consumer + 1 producer warpgroup of which one warp
+// works) at 168 registers, then the consumers grow to 232 and the producer warpgroup shrinks to 40 (setmaxnreg):
+// per sub-partition 2 x 32 x 232 + 32 x 40 = 16 128 <= 16 384.
+constexpr int NCONS = NWM * NWN, NTHREADS = (NCONS + 4) * 32;
+constexpr int REG_CONSUMER = 232, REG_PRODUCER = 40;
+constexpr int NBAR = 2 * STAGES + 2 * BSTAGES;
+constexpr size_t SMEM_BYTES = (size_t)(STAGES * A_STAGE + BSTAGES * B_STAGE) * sizeof(cplx) + NBAR * sizeof(uint64_t);
+static_assert(NCONS == 8, "two consumer warpgroups");
+static_assert(NWM * QA * 8 == TM && NWN * QB * 8 == TN, "warp grid must cover the CTA tile");
+}  // namespace m3
+
+__global__ void __launch_bounds__(m3::NTHREADS, 1) zgemm3m_dmma_kernel(ZgemmParams p) {
+    constexpr int TM = m3::TM, TN = m3::TN, KC = m3::KC, STAGES = m3::STAGES, KCB = m3::KCB, BSTAGES = m3::BSTAGES, LDSA = m3::LDSA,
+                  LDSB = m3::LDSB, A_STAGE = m3::A_STAGE, B_STAGE = m3::B_STAGE, QA = m3::QA, QB = m3::QB, NWN = m3::NWN,
+                  NCONS = m3::NCONS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* sA = reinterpret_cast<cplx*>(smem_raw);
+    cplx* sB = sA + STAGES * A_STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + BSTAGES * B_STAGE);
+    uint64_t* empty = full + STAGES;
+    uint64_t* bfull = empty + STAGES;
+    uint64_t* bempty = bfull + BSTAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KT = (p.K + KC - 1) / KC;
+    constexpr int APB = KCB / KC;
+    const int tiles_m = (p.M + TM - 1) / TM, tiles_n = (p.N + TN - 1) / TN;
+    const long long ntiles = (long long)tiles_m * tiles_n * p.batch;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+        for (int s = 0; s < BSTAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], NCONS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= NCONS) {
+        // ---------------- producer warpgroup: one working warp ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(m3::REG_PRODUCER));
+        if (warp != NCONS) return;
+        long long it = 0, ib = 0;
+        const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int mt = (int)(tile % tiles_m), nt = (int)((tile / tiles_m) % tiles_n), bz = (int)(tile / ((long long)tiles_m * tiles_n));
+            const int m0 = mt * TM, n0 = nt * TN;
+            const cplx* A = p.A + (long long)bz * p.strideA;
+            const cplx* B = p.B + (long long)bz * p.strideB;
+            const int rows_valid = min(TM, p.M - m0), cols_valid = min(TN, p.N - n0);
+            if (p.beta) {
+                // warm L2 with THIS tile's C: the consumers add it in their epilogue, about one tile time from now
+                const cplx* C2 = p.C + (long long)bz * p.strideC + m0 + (long long)n0 * p.ldc;
+                for (int j = lane; j < cols_valid; j += 32)
+                    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(C2 + (long long)j * p.ldc),
+                                 "r"((uint32_t)(rows_valid * sizeof(cplx))), "l"(stream) : "memory");
+            }
+            for (int kt = 0; kt < KT; ++kt, ++it) {
+                if (kt % APB == 0) {
+                    const int sb = (int)(ib % BSTAGES), kb0 = kt * KC;
+                    const int kvb = min(KCB, p.K - kb0);
+                    if (ib >= BSTAGES) mbar_wait(&bempty[sb], (uint32_t)(((ib / BSTAGES) - 1) & 1));
+                    if (lane == 0) mbar_expect_tx(&bfull[sb], (uint32_t)(cols_valid * kvb * sizeof(cplx)));
+                    __syncwarp();
+                    cplx* b_s = sB + sb * B_STAGE;
+                    for (int j = lane; j < cols_valid; j += 32)
+                        bulk_g2s(b_s + j * LDSB, B + kb0 + (long long)(n0 + j) * p.ldb, (uint32_t)(kvb * sizeof(cplx)), &bfull[sb], keep);
+                    ++ib;
+                }
+                const int s = (int)(it % STAGES), k0 = kt * KC;
+                const int kv = min(KC, p.K - k0);
+                if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1));
+                if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(kv * rows_valid * sizeof(cplx)));
+                __syncwarp();
+                if (lane < kv)
+                    bulk_g2s(sA + s * A_STAGE + lane * LDSA, A + m0 + (long long)(k0 + lane) * p.lda,
+                             (uint32_t)(rows_valid * sizeof(cplx)), &full[s], keep);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(m3::REG_CONSUMER));
+    const int wm = warp / NWN, wn = warp % NWN;
+    const int g = lane >> 2, t = lane & 3;         // DMMA fragment coordinates: A[g][t], B[t][g], C[g][2t, 2t+1]
+    const long long sflip = (p.negate ? 1LL : 0LL) << 63;
+    const int arow = wm * (8 * QA) + g;
+    const int bcol = wn * (8 * QB) + g;
+    long long it = 0, ib = 0;
+    const uint64_t stream = l2_policy_evict_first();
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int mt = (int)(tile % tiles_m), nt = (int)((tile / tiles_m) % tiles_n), bz = (int)(tile / ((long long)tiles_m * tiles_n));
+        const int m0 = mt * TM, n0 = nt * TN;
+        cplx* C = p.C + (long long)bz * p.strideC;
+        double p1[QA][QB][2], p2[QA][QB][2], p3[QA][QB][2];
+#pragma unroll
+        for (int qa = 0; qa < QA; ++qa)
+#pragma unroll
+            for (int qb = 0; qb < QB; ++qb)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) { p1[qa][qb][j] = 0.0; p2[qa][qb][j] = 0.0; p3[qa][qb][j] = 0.0; }
+        const double2* b_s = nullptr;
+        int sb = 0;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+            if (kt % APB == 0) {
+                sb = (int)(ib % BSTAGES);
+                mbar_wait(&bfull[sb], (uint32_t)((ib / BSTAGES) & 1));
+                b_s = reinterpret_cast<const double2*>(sB + sb * B_STAGE);
+                ++ib;
+            }
+            const int s = (int)(it % STAGES);
+            const int kv = min(KC, p.K - kt * KC);
+            const int kboff = (kt % APB) * KC;
+            mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+            const double2* a_s = reinterpret_cast<const double2*>(sA + s * A_STAGE);
+            if (kv == KC) {
+#pragma unroll
+                for (int ks = 0; ks < KC / 4; ++ks) {
+                    const int kc = 4 * ks + t;          // this lane's complex k of the k4 step
+                    double br[QB], bi[QB], bs[QB];
+#pragma unroll
+                    for (int qb = 0; qb < QB; ++qb) {
+                        const double2 b = b_s[(bcol + 8 * qb) * LDSB + kboff + kc];
+                        br[qb] = __longlong_as_double(__double_as_longlong(b.x) ^ sflip);
+                        bi[qb] = __longlong_as_double(__double_as_longlong(b.y) ^ sflip);
+                        bs[qb] = br[qb] + bi[qb];
+                    }
+#pragma unroll
+                    for (int qa = 0; qa < QA; ++qa) {
+                        const double2 a = a_s[kc * LDSA + arow + 8 * qa];
+                        const double as = a.x + a.y;
+#pragma unroll
+                        for (int qb = 0; qb < QB; ++qb) {
+                            dmma884(p1[qa][qb][0], p1[qa][qb][1], a.x, br[qb]);
+                            dmma884(p2[qa][qb][0], p2[qa][qb][1], a.y, bi[qb]);
+                            dmma884(p3[qa][qb][0], p3[qa][qb][1], as, bs[qb]);
+                        }
+                    }
+                }
+            } else {
+                // K tail: complex k >= kv contribute exact zeros (both fragments are cleared in registers)
+                for (int ks = 0; 4 * ks < kv; ++ks) {
+                    const int kc = 4 * ks + t;
+                    const bool ok = kc < kv;
+                    double br[QB], bi[QB], bs[QB];
+#pragma unroll
+                    for (int qb = 0; qb < QB; ++qb) {
+                        const double2 b = ok ? b_s[(bcol + 8 * qb) * LDSB + kboff + kc] : make_double2(0.0, 0.0);
+                        br[qb] = __longlong_as_double(__double_as_longlong(b.x) ^ sflip);
+                        bi[qb] = __longlong_as_double(__double_as_longlong(b.y) ^ sflip);
+                        bs[qb] = br[qb] + bi[qb];
+                    }
+#pragma unroll
+                    for (int qa = 0; qa < QA; ++qa) {
+                        const double2 a = ok ? a_s[kc * LDSA + arow + 8 * qa] : make_double2(0.0, 0.0);
+                        const double as = a.x + a.y;
+#pragma unroll
+                        for (int qb = 0; qb < QB; ++qb) {
+                            dmma884(p1[qa][qb][0], p1[qa][qb][1], a.x, br[qb]);
+                            dmma884(p2[qa][qb][0], p2[qa][qb][1], a.y, bi[qb]);
+                            dmma884(p3[qa][qb][0], p3[qa][qb][1], as, bs[qb]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[s]);
+                if (kt % APB == APB - 1 || kt == KT - 1) mbar_arrive(&bempty[sb]);
+            }
+        }
+        // epilogue: Re = P1 - P2, Im = (P3 - P1) - P2, plus C when accumulating (L2 hits: prefetched by the producer).
+        // The C loads of row block qa + 1 are issued before the stores of row block qa, so one L2 latency is exposed per
+        // tile instead of one per row block.
+        const int er = m0 + wm * (8 * QA) + g, ec = n0 + wn * (8 * QB) + 2 * t;
+        cplx cv[2][QB][2];
+        auto load_c = [&](int qa, cplx (&dst)[QB][2]) {
+#pragma unroll
+            for (int qb = 0; qb < QB; ++qb)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int r = er + 8 * qa, c = ec + 8 * qb + j;
+                    dst[qb][j] = (p.beta && r < p.M && c < p.N) ? ld_stream(&C[r + (long long)c * p.ldc], stream) : cmake(0.0, 0.0);
+                }
+        };
+        load_c(0, cv[0]);
+#pragma unroll
+        for (int qa = 0; qa < QA; ++qa) {
+            if (qa + 1 < QA) load_c(qa + 1, cv[(qa + 1) & 1]);
+#pragma unroll
+            for (int qb = 0; qb < QB; ++qb)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int r = er + 8 * qa, c = ec + 8 * qb + j;
+                    if (r < p.M && c < p.N) {
+                        const double re = (p1[qa][qb][j] - p2[qa][qb][j]) + cv[qa & 1][qb][j].x;
+                        const double im = ((p3[qa][qb][j] - p1[qa][qb][j]) - p2[qa][qb][j]) + cv[qa & 1][qb][j].y;
+                        st_stream(&C[r + (long long)c * p.ldc], cmake(re, im), stream);
+                    }
+                }
+        }
+    }
+}
+
 // Independent FP64-FMA implementation (16 x 16 tiles) -- test cross-check only.
 __global__ void __launch_bounds__(256) zgemm_simple_kernel(ZgemmParams p) {
     __shared__ cplx sa[16][17], sb[16][17];
@@ -304,6 +526,21 @@ static cudaError_t launch_cfg(const ZgemmParams& p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_3m(const ZgemmParams& p, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(zgemm3m_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m3::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const long long ntiles = (long long)((p.M + m3::TM - 1) / m3::TM) * ((p.N + m3::TN - 1) / m3::TN) * p.batch;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = MAUS_SM_COUNT_B200; }
+    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);          // persistent: one CTA per SM
+    zgemm3m_dmma_kernel<<<grid, m3::NTHREADS, m3::SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
 static int g_zgemm_cfg = -1;
 void zgemm_set_config(int cfg) { g_zgemm_cfg = cfg; }
 
@@ -314,6 +551,7 @@ cudaError_t zgemm_dmma_launch(const ZgemmParams& p, cudaStream_t stream) {
         const char* e = getenv("MAUS_GEMM_CFG");
         g_zgemm_cfg = e ? atoi(e) : 0;
     }
+    if (p.algo3m) return launch_3m(p, stream);              // 128-row tiles: also valid for the in-place U12 solve
     if ((const void*)p.C == (const void*)p.B) return launch_cfg<128, 8>(p, stream);   // in-place (U12 = L11^-1 A12): one row tile must own all rows
     if (g_zgemm_cfg == 1) return launch_cfg<128, 4>(p, stream);
     if (g_zgemm_cfg == 3) return launch_cfg<64, 8>(p, stream);   // 64 x 64 tiles, 2 CTAs / SM

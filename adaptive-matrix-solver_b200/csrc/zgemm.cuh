@@ -9,6 +9,7 @@ struct ZgemmParams {
     int M, N, K, batch;
     int beta;      // 0: C = s*A*B        1: C = C + s*A*B
     int negate;    // s = -1 when set, else +1
+    int algo3m;    // 1: three-real-product complex arithmetic (6 instead of 8 flops per complex FMA; LU updates)
 };
 
 // Tensor-pipe kernel (any M, N, K >= 1).  In-place use (C == B) is supported for M <= 128: it is routed to the 128-row tile configuration so one CTA owns all rows of its columns.

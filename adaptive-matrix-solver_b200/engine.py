@@ -238,13 +238,14 @@ class MausEngine:
         return resid
 
     def debug_zgemm(self, A, B, Cm, beta=0, negate=False, use_dmma=True):
-        """Parity hook: batched column-major complex GEMM; A [batch][K][M] (i.e. column-major M x K), etc."""
+        """Parity hook: batched column-major complex GEMM; A [batch][K][M] (i.e. column-major M x K), etc.
+        use_dmma: 0 plain FP64-FMA kernel, 1 tensor-pipe kernel (4 real products), 2 tensor-pipe 3M kernel of the LU."""
         A = _as_c128(A); B = _as_c128(B); Cm = _as_c128(Cm).copy()
         batch, K, M = A.shape
         _, N, K2 = B.shape
         assert K2 == K and Cm.shape == (batch, N, M)
         self._check(self._lib.maus_debug_zgemm(self._h, M, N, K, batch, _dp(A), _dp(B), _dp(Cm), int(beta),
-                                               1 if negate else 0, 1 if use_dmma else 0))
+                                               1 if negate else 0, int(use_dmma)))
         return Cm
 
     # -- SVD power-sweep branch (AMS:227-255, 300-301) -------------------------------------------------------

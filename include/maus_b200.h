@@ -171,7 +171,8 @@ int maus_rs_gmres(maus_ctx* ctx, int64_t C, const double* sigma, const double* p
                   const double* RHS_local, double* X_local_out, int32_t* status_out, int32_t* iters_out);
 
 /* debug / parity: C = beta*C + s*A*B on column-major complex128 host matrices (A: M x K, B: K x N, C: M x N,
- * `batch` of each, densely packed) through the tensor-pipe kernel (use_dmma != 0) or the plain FP64-FMA kernel. */
+ * `batch` of each, densely packed) through the tensor-pipe kernel (use_dmma = 1; 2 = the three-real-product
+ * variant used by the LU trailing updates) or the plain FP64-FMA kernel (use_dmma = 0). */
 int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, const double* A, const double* B, double* C,
                      int beta, int negate, int use_dmma);
 

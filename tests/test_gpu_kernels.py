@@ -34,6 +34,9 @@ def test_zgemm_dmma_matches_numpy(eng, M, N, K, batch, beta, negate):
     scale = np.abs(A).max() * np.abs(B).max() * K + 1
     assert np.abs(out - ref).max() <= 1e-14 * scale
     assert np.abs(out2 - ref).max() <= 1e-14 * scale
+    # the LU's 3M kernel (three real products): normwise the same bound, a different rounding pattern
+    out3 = eng.debug_zgemm(Acm, Bcm, Ccm, beta=beta, negate=negate, use_dmma=2).transpose(0, 2, 1)
+    assert np.abs(out3 - ref).max() <= 2e-14 * scale
 
 
 @pytest.mark.parametrize("n", [1, 2, 5, 8, 16, 100, 127, 128, 129, 256, 300, 520])
