@@ -17,6 +17,7 @@ struct MatrixSlot {
     int* colidx = nullptr;       // nnz
     cplx* vals = nullptr;        // nnz
     cplx* diag = nullptr;        // n, diagonal of the matrix (Jacobi preconditioner, AMS:67)
+    cplx* pack = nullptr;        // [n][4] interleaved copy of up to 4 candidate vectors for the SpMM gathers (spmv.cu)
     double amax = 0.0;           // max |a_ij| (cabs1), used to gate the sub-ulp Psi perturbation in matvec-only paths
 };
 
@@ -24,6 +25,7 @@ struct ProfAccum {
     bool enabled = false;
     std::vector<cudaEvent_t> ev;     // pairs
     std::vector<int> kind;           // MAUS_PROF_* (include/maus_b200.h)
+    std::vector<long long> tag;      // optional per-launch tag (GEMM shape), printed when MAUS_GEMM_LOG is set
     size_t used = 0;
     double ms[8] = {0};
     long long launches[8] = {0};
@@ -85,6 +87,7 @@ int maus_ensure_population(maus_ctx* ctx, long long C);
 // profiling brackets (no-ops unless enabled)
 int prof_begin(maus_ctx* ctx, int kind, double work);
 void prof_end(maus_ctx* ctx, int handle);
+void prof_tag(maus_ctx* ctx, int handle, int M, int N, int K, int batch);
 
 // Y[c] = A(slot) * V[c] for C candidates: dense -> DMMA GEMM (C > 8) or HBM-bound GEMV; sparse -> CSR SpMM
 int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cplx* Y, long long ldy, long long C);

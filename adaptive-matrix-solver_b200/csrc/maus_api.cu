@@ -31,25 +31,40 @@ void maus_dev_free(maus_ctx* ctx, void* p, size_t bytes) {
     if (p) { cudaFree(p); ctx->bytes_held -= (long long)bytes; }
 }
 
+// accumulate the recorded event pairs (stream must be idle); MAUS_GEMM_LOG=1 prints every tagged launch to stderr
+static void prof_drain(maus_ctx* ctx) {
+    ProfAccum& pr = ctx->prof;
+    static int log = -1;
+    if (log < 0) { const char* e = getenv("MAUS_GEMM_LOG"); log = (e && atoi(e)) ? 1 : 0; }
+    for (size_t i = 0; i + 1 < pr.used; i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pr.ev[i], pr.ev[i + 1]);
+        pr.ms[pr.kind[i / 2]] += ms;
+        const long long tg = pr.tag[i / 2];
+        if (log && tg)
+            fprintf(stderr, "gemm M %lld N %lld K %lld batch %lld ms %.4f\n", (tg >> 40) & 0xffff, (tg >> 24) & 0xffff, (tg >> 8) & 0xffff,
+                    tg & 0xff, ms);
+    }
+    pr.used = 0;
+}
+void prof_tag(maus_ctx* ctx, int h, int M, int N, int K, int batch) {
+    if (h >= 0) ctx->prof.tag[h / 2] = ((long long)M << 40) | ((long long)N << 24) | ((long long)K << 8) | (long long)(batch & 0xff);
+}
+
 int prof_begin(maus_ctx* ctx, int kind, double work) {
     ProfAccum& pr = ctx->prof;
     if (!pr.enabled) return -1;
     if (pr.used + 2 > pr.ev.size()) {
-        // drain: accumulate what is recorded so far
         cudaStreamSynchronize(ctx->stream);
-        for (size_t i = 0; i + 1 < pr.used; i += 2) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, pr.ev[i], pr.ev[i + 1]);
-            pr.ms[pr.kind[i / 2]] += ms;
-        }
-        pr.used = 0;
+        prof_drain(ctx);
         if (pr.ev.empty()) {
-            pr.ev.resize(4096); pr.kind.resize(2048);
+            pr.ev.resize(4096); pr.kind.resize(2048); pr.tag.resize(2048);
             for (auto& e : pr.ev) cudaEventCreate(&e);
         }
     }
     int h = (int)pr.used;
     pr.kind[h / 2] = kind;
+    pr.tag[h / 2] = 0;
     pr.launches[kind] += 1;
     pr.work[kind] += work;
     cudaEventRecord(pr.ev[h], ctx->stream);
@@ -122,6 +137,7 @@ static void free_slot(maus_ctx* ctx, MatrixSlot& s, long long n) {
     maus_dev_free(ctx, s.rm, n * n * sizeof(cplx)); maus_dev_free(ctx, s.cm, n * n * sizeof(cplx));
     maus_dev_free(ctx, s.rowptr, (n + 1) * 8); maus_dev_free(ctx, s.colidx, s.nnz * 4);
     maus_dev_free(ctx, s.vals, s.nnz * sizeof(cplx)); maus_dev_free(ctx, s.diag, n * sizeof(cplx));
+    if (s.pack) maus_dev_free(ctx, s.pack, n * 4 * sizeof(cplx));
     s = MatrixSlot();
 }
 
@@ -225,12 +241,7 @@ extern "C" int maus_profile_read(maus_ctx* ctx, double* lu_gemm_ms, int64_t* lu_
     if (!ctx) return MAUS_E_ARG;
     MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ProfAccum& pr = ctx->prof;
-    for (size_t i = 0; i + 1 < pr.used; i += 2) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, pr.ev[i], pr.ev[i + 1]);
-        pr.ms[pr.kind[i / 2]] += ms;
-    }
-    pr.used = 0;
+    prof_drain(ctx);
     if (lu_gemm_ms) *lu_gemm_ms = pr.ms[0];
     if (lu_gemm_launches) *lu_gemm_launches = pr.launches[0];
     if (lu_gemm_flops) *lu_gemm_flops = pr.work[0];
@@ -405,9 +416,10 @@ int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cpl
     }
     if (s.sparse) {
         int h = prof_begin(ctx, MAUS_PROF_MATVEC, (double)((C + 3) / 4) * (20.0 * s.nnz + 8.0 * (n + 1)) + 32.0 * n * C);
-        MAUS_CUDA(ctx, csr_spmm(s.rowptr, s.colidx, s.vals, V, ldv, Y, ldy, n, (int)C, ctx->stream));
+        if (C > 1 && !s.pack) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.pack, (size_t)n * 4 * sizeof(cplx)));
+        MAUS_CUDA(ctx, csr_spmm(s.rowptr, s.colidx, s.vals, V, ldv, Y, ldy, n, n, (int)C, C > 1 ? s.pack : nullptr, ctx->stream));
         prof_end(ctx, h);
-        ctx->launches += (C + 3) / 4;
+        ctx->launches += (C + 3) / 4 + (C > 1 ? (C + 3) / 4 - (C % 4 == 1 ? 1 : 0) : 0);   // SpMM passes + pack passes
         return MAUS_OK;
     }
     return maus_fail(ctx, MAUS_E_STATE, "matrix slot not set");
@@ -479,6 +491,7 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
             p.M = M; p.N = N; p.K = K; p.batch = nb; p.beta = beta; p.negate = negate;
             p.algo3m = lu_use_3m();
             int h = prof_begin(ctx, MAUS_PROF_LU_GEMM, 8.0 * M * (double)N * K * nb);
+            prof_tag(ctx, h, M, N, K, nb);
             cudaError_t e = zgemm_dmma_launch(p, st);
             prof_end(ctx, h);
             ctx->launches += 1;

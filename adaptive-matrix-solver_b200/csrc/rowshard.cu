@@ -51,6 +51,7 @@ struct RowShard {
     long long* rowptr = nullptr; int* colidx = nullptr; cplx* vals = nullptr; cplx* diag = nullptr;
     double amax = 0.0;
     cplx* xfull = nullptr; long long xcap = 0;      // [C][n] gathered input of the matvec
+    cplx* pack = nullptr;                           // [n][4] interleaved copy for the SpMM gathers
     cplx *V = nullptr, *X = nullptr, *Y = nullptr, *sigma = nullptr; double* psi = nullptr; unsigned char* jac = nullptr;
     int *status = nullptr, *iters = nullptr; long long Ccap = 0;
 };
@@ -64,7 +65,7 @@ struct RowShard {
 void maus_rowshard_free(maus_ctx* ctx) {
     RowShard* rs = (RowShard*)ctx->rowshard;
     if (!rs) return;
-    cudaFree(rs->rowptr); cudaFree(rs->colidx); cudaFree(rs->vals); cudaFree(rs->diag); cudaFree(rs->xfull);
+    cudaFree(rs->rowptr); cudaFree(rs->colidx); cudaFree(rs->vals); cudaFree(rs->diag); cudaFree(rs->xfull); cudaFree(rs->pack);
     cudaFree(rs->V); cudaFree(rs->X); cudaFree(rs->Y); cudaFree(rs->sigma); cudaFree(rs->psi); cudaFree(rs->jac);
     cudaFree(rs->status); cudaFree(rs->iters);
     if (rs->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(rs->comm);
@@ -137,10 +138,11 @@ extern "C" int maus_set_csr_rowblock(maus_ctx* ctx, int64_t n, int64_t row0, int
 static int rs_ensure(maus_ctx* ctx, RowShard* rs, long long C) {
     if (C <= rs->Ccap) return MAUS_OK;
     MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(rs->xfull); cudaFree(rs->V); cudaFree(rs->X); cudaFree(rs->Y); cudaFree(rs->sigma); cudaFree(rs->psi);
+    cudaFree(rs->xfull); cudaFree(rs->pack); cudaFree(rs->V); cudaFree(rs->X); cudaFree(rs->Y); cudaFree(rs->sigma); cudaFree(rs->psi);
     cudaFree(rs->jac); cudaFree(rs->status); cudaFree(rs->iters);
     const long long cap = std::max<long long>(C, 4);
     MAUS_CUDA(ctx, cudaMalloc(&rs->xfull, (size_t)cap * rs->n * sizeof(cplx)));
+    MAUS_CUDA(ctx, cudaMalloc(&rs->pack, (size_t)4 * rs->n * sizeof(cplx)));
     MAUS_CUDA(ctx, cudaMalloc(&rs->V, (size_t)cap * rs->nloc * sizeof(cplx)));
     MAUS_CUDA(ctx, cudaMalloc(&rs->X, (size_t)cap * rs->nloc * sizeof(cplx)));
     MAUS_CUDA(ctx, cudaMalloc(&rs->Y, (size_t)cap * rs->nloc * sizeof(cplx)));
@@ -161,7 +163,7 @@ static int rs_matvec(maus_ctx* ctx, RowShard* rs, const cplx* v, long long ldv, 
     for (long long c = 0; c < C; ++c)
         MAUS_NCCL(ctx, g_nccl.AllGather(v + c * ldv, rs->xfull + c * rs->n, (size_t)rs->nloc * 2, ncclDouble, rs->comm, st));
     MAUS_NCCL(ctx, g_nccl.GroupEnd());
-    MAUS_CUDA(ctx, csr_spmm(rs->rowptr, rs->colidx, rs->vals, rs->xfull, rs->n, z, ldz, rs->nloc, (int)C, st));
+    MAUS_CUDA(ctx, csr_spmm(rs->rowptr, rs->colidx, rs->vals, rs->xfull, rs->n, z, ldz, rs->nloc, rs->n, (int)C, rs->pack, st));
     prof_end(ctx, h);
     ctx->launches += (C + 3) / 4;
     return MAUS_OK;

@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(RED_NT) nan_scan_kernel(const cplx* __restrict
 // ---- HBM-bound batched matvec: Y[c] = A_rm * V[c] -------------------------------------------------------------
 // One warp per matrix row (coalesced 512 B row segments, warp-shuffle dot-product reduction); CB candidate vectors
 // are staged through shared memory in chunks so the matrix is streamed from HBM exactly once per CB candidates.
-constexpr int GV_NT = 256, GV_JC = 512;
-template <int CB, int RPW>      // CB candidates per pass, RPW rows per warp (the staged vector entries are reused across rows)
+constexpr int GV_JC = 512;
+// CB candidates per pass, RPW rows per warp (the staged vector entries are reused across rows: half the LDS traffic at
+// RPW = 2), GV_NT threads (128-thread CTAs keep the grid at several waves when RPW = 2 is used below n = 8192)
+template <int CB, int RPW, int GV_NT>
 __global__ void __launch_bounds__(GV_NT) gemv_rowmajor_kernel(const cplx* __restrict__ A, const cplx* __restrict__ V,
                                                               long long ldv, cplx* __restrict__ Y, long long ldy, int nrows,
                                                               int n, int c0, int ncand) {
@@ -265,30 +267,32 @@ cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int 
     return cudaGetLastError();
 }
 
-template <int RPW>
+template <int RPW, int GV_NT>
 static void gemv_launch(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int nrows, int n, int C,
                         cudaStream_t stream) {
     const int rows = RPW * (GV_NT / 32);
     const int grid = (nrows + rows - 1) / rows;
     for (int c0 = 0; c0 < C; c0 += 4) {
         const int nc = (C - c0 < 4) ? (C - c0) : 4;
-        if (nc == 1) gemv_rowmajor_kernel<1, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, nrows, n, c0, nc);
-        else if (nc == 2) gemv_rowmajor_kernel<2, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, nrows, n, c0, nc);
-        else gemv_rowmajor_kernel<4, RPW><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, nrows, n, c0, nc);
+        if (nc == 1) gemv_rowmajor_kernel<1, RPW, GV_NT><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, nrows, n, c0, nc);
+        else if (nc == 2) gemv_rowmajor_kernel<2, RPW, GV_NT><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, nrows, n, c0, nc);
+        else gemv_rowmajor_kernel<4, RPW, GV_NT><<<grid, GV_NT, 0, stream>>>(A_rm, V, ldv, Y, ldy, nrows, n, c0, nc);
     }
 }
 
 cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
                               cudaStream_t stream) {
     // grid sized so that several waves of CTAs cover the 148 SMs: 8 rows per CTA below n = 8192, 16 above
-    if (n >= 8192) gemv_launch<2>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
-    else gemv_launch<1>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
+    if (n >= 8192) gemv_launch<2, 256>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
+    else if (C >= 2 && n >= 2048) gemv_launch<2, 128>(A_rm, V, ldv, Y, ldy, n, n, C, stream);   // several candidates: LDS-bound at RPW = 1
+    else gemv_launch<1, 256>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
     return cudaGetLastError();
 }
 
 cudaError_t vec_gemv_rect(const cplx* A_rm, int nrows, int ncols, const cplx* V, long long ldv, cplx* Y, long long ldy, int C,
                           cudaStream_t stream) {
-    if (nrows >= 8192) gemv_launch<2>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
-    else gemv_launch<1>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
+    if (nrows >= 8192) gemv_launch<2, 256>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
+    else if (C >= 2 && nrows >= 2048) gemv_launch<2, 128>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
+    else gemv_launch<1, 256>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
     return cudaGetLastError();
 }

@@ -271,10 +271,6 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
 //   the 128-bit fragment loads conflict free per quarter warp.  C is added in the epilogue (accumulators start at 0).
 namespace m3 {
 constexpr int TM = 128, TN = 48;
-constexpr int KC = 16, STAGES = 3;
-constexpr int KCB = 32, BSTAGES = 2;
-constexpr int LDSA = TM + 2, LDSB = KCB + 4;
-constexpr int A_STAGE = KC * LDSA, B_STAGE = TN * LDSB;
 constexpr int QA = 4, QB = 3, NWM = 4, NWN = 2;
 // Register budget: the register file is split per SM sub-partition (16 K registers each), so a 9th warp would cap every
 // thread at 168 registers.  The CTA is launched as three warpgroups (2 consumer + 1 producer warpgroup of which one warp
@@ -282,15 +278,24 @@ constexpr int QA = 4, QB = 3, NWM = 4, NWN = 2;
 // per sub-partition 2 x 32 x 232 + 32 x 40 = 16 128 <= 16 384.
 constexpr int NCONS = NWM * NWN, NTHREADS = (NCONS + 4) * 32;
 constexpr int REG_CONSUMER = 232, REG_PRODUCER = 40;
-constexpr int NBAR = 2 * STAGES + 2 * BSTAGES;
-constexpr size_t SMEM_BYTES = (size_t)(STAGES * A_STAGE + BSTAGES * B_STAGE) * sizeof(cplx) + NBAR * sizeof(uint64_t);
 static_assert(NCONS == 8, "two consumer warpgroups");
 static_assert(NWM * QA * 8 == TM && NWN * QB * 8 == TN, "warp grid must cover the CTA tile");
+// pipeline shape: A slabs of KC complex k (KC bulk copies of TM*16 B), B slabs of KCB complex k (TN copies of KCB*16 B)
+template <int KC_, int STAGES_, int KCB_, int BSTAGES_> struct Pipe {
+    static constexpr int KC = KC_, STAGES = STAGES_, KCB = KCB_, BSTAGES = BSTAGES_;
+    static constexpr int LDSA = TM + 2, LDSB = KCB + 4;        // strides = 2 / 4 (mod 8) complex: conflict-free LDS.128
+    static constexpr int A_STAGE = KC * LDSA, B_STAGE = TN * LDSB;
+    static constexpr int NBAR = 2 * STAGES + 2 * BSTAGES;
+    static constexpr size_t SMEM_BYTES = (size_t)(STAGES * A_STAGE + BSTAGES * B_STAGE) * sizeof(cplx) + NBAR * sizeof(uint64_t);
+    static_assert(KC <= 32 && KCB % KC == 0 && KC % 4 == 0, "slab shapes");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
 }  // namespace m3
 
+template <class PP>
 __global__ void __launch_bounds__(m3::NTHREADS, 1) zgemm3m_dmma_kernel(ZgemmParams p) {
-    constexpr int TM = m3::TM, TN = m3::TN, KC = m3::KC, STAGES = m3::STAGES, KCB = m3::KCB, BSTAGES = m3::BSTAGES, LDSA = m3::LDSA,
-                  LDSB = m3::LDSB, A_STAGE = m3::A_STAGE, B_STAGE = m3::B_STAGE, QA = m3::QA, QB = m3::QB, NWN = m3::NWN,
+    constexpr int TM = m3::TM, TN = m3::TN, KC = PP::KC, STAGES = PP::STAGES, KCB = PP::KCB, BSTAGES = PP::BSTAGES, LDSA = PP::LDSA,
+                  LDSB = PP::LDSB, A_STAGE = PP::A_STAGE, B_STAGE = PP::B_STAGE, QA = m3::QA, QB = m3::QB, NWN = m3::NWN,
                   NCONS = m3::NCONS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* sA = reinterpret_cast<cplx*>(smem_raw);
@@ -526,10 +531,11 @@ static cudaError_t launch_cfg(const ZgemmParams& p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-static cudaError_t launch_3m(const ZgemmParams& p, cudaStream_t stream) {
+template <class PP>
+static cudaError_t launch_3m_cfg(const ZgemmParams& p, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(zgemm3m_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m3::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(zgemm3m_dmma_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -537,8 +543,21 @@ static cudaError_t launch_3m(const ZgemmParams& p, cudaStream_t stream) {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = MAUS_SM_COUNT_B200; }
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);          // persistent: one CTA per SM
-    zgemm3m_dmma_kernel<<<grid, m3::NTHREADS, m3::SMEM_BYTES, stream>>>(p);
+    zgemm3m_dmma_kernel<PP><<<grid, m3::NTHREADS, PP::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
+}
+
+static cudaError_t launch_3m(const ZgemmParams& p, cudaStream_t stream) {
+    static int cfg = -1;
+    if (cfg < 0) { const char* e = getenv("MAUS_3M_CFG"); cfg = e ? atoi(e) : 0; }
+    switch (cfg) {
+        case 1: return launch_3m_cfg<m3::Pipe<16, 4, 32, 2>>(p, stream);
+        case 2: return launch_3m_cfg<m3::Pipe<16, 3, 64, 2>>(p, stream);
+        case 3: return launch_3m_cfg<m3::Pipe<32, 2, 32, 2>>(p, stream);
+        case 4: return launch_3m_cfg<m3::Pipe<32, 2, 32, 3>>(p, stream);
+        case 5: return launch_3m_cfg<m3::Pipe<16, 3, 32, 2>>(p, stream);
+        default: return launch_3m_cfg<m3::Pipe<32, 2, 32, 3>>(p, stream);     // measured best (profiles/README_r01.md)
+    }
 }
 
 static int g_zgemm_cfg = -1;
