@@ -126,6 +126,7 @@ def lu_gemm_algorithmic(n, cand, nb=128, group=4, leaf=64):
 # DRAM traffic of the GEMM launches measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum over the 151 LU launches
 # + 2 batched A*V launches of one generation at n = 4096 with 16 candidates: profiles/launches_r01_final.csv), per candidate
 NCU_GEMM_DRAM_BYTES_PER_CANDIDATE = (33.565e9 + 13.110e9) / 16.0
+NCU_GEMM_TRAFFIC_SOURCE = "profiles/launches_r01_final.csv"
 
 
 def vector_alpha_update(alpha, resid, prev):
@@ -242,12 +243,20 @@ def run_b200(args):
     achieved = prof["lu_gemm_flops"] / gemm_s / 1e12 if gemm_s > 0 else 0.0
     n_launch, alg_flops, alg_bytes = lu_gemm_algorithmic(n, C_)
     per_launch = max(1, prof["lu_gemm_launches"] // args.steps)
-    roofline = {"kernel": "zgemm_dmma_kernel (LU trailing update + U12 solve)", "bound": "tensor",
+    use_3m = os.environ.get("MAUS_GEMM_3M", "1") != "0"
+    exec_ratio = 0.75 if use_3m else 1.0          # 3M: 6 instead of 8 real flops per complex multiply-add reach the DMMA pipe
+    roofline = {"kernel": ("zgemm3m_dmma_kernel" if use_3m else "zgemm_dmma_kernel") + " (LU trailing update + U12 solve)",
+                "bound": "tensor",
                 "achieved": round(achieved, 3), "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": round(achieved / FP64_PEAK_TFLOPS, 4),
+                "note": ("achieved = ALGORITHMIC flops (8 per complex multiply-add, SURVEY.md 8d) / kernel time; the kernel forms every "
+                         "complex product from three real products (3M), so only 0.75 x that rate executes on the FP64 tensor pipe: "
+                         "frac can exceed 1, pipe_frac is the hardware utilisation") if use_3m else None,
+                "executed_tflops": round(achieved * exec_ratio, 3),
+                "pipe_frac": round(achieved * exec_ratio / FP64_PEAK_TFLOPS, 4),
                 "traffic": round(NCU_GEMM_DRAM_BYTES_PER_CANDIDATE * C_ / per_launch) if n == 4096 else None,
                 "traffic_unit": "bytes per launch (ncu dram read+write, average over the LU GEMM launches of a generation; "
-                                "measured at 16 candidates and scaled by the candidate count, profiles/launches_r01_final.csv)",
+                                "measured at 16 candidates and scaled by the candidate count, " + NCU_GEMM_TRAFFIC_SOURCE + ")",
                 "algorithmic_flops_per_launch": round(alg_flops / n_launch), "algorithmic_bytes_per_launch": round(alg_bytes / n_launch),
                 "peak_source": "own measurement (FP64 DMMA, profiles/fp64_peak_r01.txt); MEASURED_PEAKS.json has no FP64 entry",
                 "share_of_step": round(gemm_s / (dev_ms / 1e3), 4) if dev_ms > 0 else None,
