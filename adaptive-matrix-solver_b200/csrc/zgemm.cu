@@ -285,8 +285,10 @@ template <int KC_, int STAGES_, int KCB_, int BSTAGES_> struct Pipe {
     static constexpr int KC = KC_, STAGES = STAGES_, KCB = KCB_, BSTAGES = BSTAGES_;
     static constexpr int LDSA = TM + 2, LDSB = KCB + 4;        // strides = 2 / 4 (mod 8) complex: conflict-free LDS.128
     static constexpr int A_STAGE = KC * LDSA, B_STAGE = TN * LDSB;
-    static constexpr int NBAR = 2 * STAGES + 2 * BSTAGES;
-    static constexpr size_t SMEM_BYTES = (size_t)(STAGES * A_STAGE + BSTAGES * B_STAGE) * sizeof(cplx) + NBAR * sizeof(uint64_t);
+    // result staging tile [TN][LDSC]: column stride = 1 (mod 4) complex makes the fragment-order STS.128 conflict free
+    static constexpr int LDSC = TM + 1, C_STAGE = TN * LDSC;
+    static constexpr int NBAR = 2 * STAGES + 2 * BSTAGES + 2;
+    static constexpr size_t SMEM_BYTES = (size_t)(STAGES * A_STAGE + BSTAGES * B_STAGE + C_STAGE) * sizeof(cplx) + NBAR * sizeof(uint64_t);
     static_assert(KC <= 32 && KCB % KC == 0 && KC % 4 == 0, "slab shapes");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
@@ -296,14 +298,17 @@ template <class PP>
 __global__ void __launch_bounds__(m3::NTHREADS, 1) zgemm3m_dmma_kernel(ZgemmParams p) {
     constexpr int TM = m3::TM, TN = m3::TN, KC = PP::KC, STAGES = PP::STAGES, KCB = PP::KCB, BSTAGES = PP::BSTAGES, LDSA = PP::LDSA,
                   LDSB = PP::LDSB, A_STAGE = PP::A_STAGE, B_STAGE = PP::B_STAGE, QA = m3::QA, QB = m3::QB, NWN = m3::NWN,
-                  NCONS = m3::NCONS;
+                  NCONS = m3::NCONS, LDSC = PP::LDSC, C_STAGE = PP::C_STAGE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* sA = reinterpret_cast<cplx*>(smem_raw);
     cplx* sB = sA + STAGES * A_STAGE;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + BSTAGES * B_STAGE);
+    cplx* sC = sB + BSTAGES * B_STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sC + C_STAGE);
     uint64_t* empty = full + STAGES;
     uint64_t* bfull = empty + STAGES;
     uint64_t* bempty = bfull + BSTAGES;
+    uint64_t* cfull = bempty + BSTAGES;          // consumers -> storer: the staged result tile is complete
+    uint64_t* cempty = cfull + 1;                // storer -> consumers: the staging tile may be overwritten
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KT = (p.K + KC - 1) / KC;
@@ -314,13 +319,41 @@ __global__ void __launch_bounds__(m3::NTHREADS, 1) zgemm3m_dmma_kernel(ZgemmPara
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
         for (int s = 0; s < BSTAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], NCONS); }
+        mbar_init(cfull, NCONS); mbar_init(cempty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp >= NCONS) {
-        // ---------------- producer warpgroup: one working warp ----------------
+        // ---------------- producer warpgroup: a loader warp and a storer warp ----------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(m3::REG_PRODUCER));
+        if (warp == NCONS + 1) {
+            // storer: the consumers park the finished tile in sC and go on with the next tile; this warp writes it out with
+            // TMA bulk operations, one per column -- a plain store (beta = 0) or an f64 add performed by the L2 (C += tile),
+            // so C never travels to the SM and no thread waits for a global round trip
+            long long tl = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+                const int mt = (int)(tile % tiles_m), nt = (int)((tile / tiles_m) % tiles_n), bz = (int)(tile / ((long long)tiles_m * tiles_n));
+                const int m0 = mt * TM, n0 = nt * TN;
+                const int rows_valid = min(TM, p.M - m0), cols_valid = min(TN, p.N - n0);
+                cplx* Cg = p.C + (long long)bz * p.strideC + m0 + (long long)n0 * p.ldc;
+                mbar_wait(cfull, (uint32_t)(tl & 1));
+                for (int j = lane; j < cols_valid; j += 32) {
+                    if (p.beta)
+                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                                     ::"l"(Cg + (long long)j * p.ldc), "r"(smem_u32(sC + j * LDSC)), "r"((uint32_t)(rows_valid * sizeof(cplx))) : "memory");
+                    else
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(Cg + (long long)j * p.ldc), "r"(smem_u32(sC + j * LDSC)), "r"((uint32_t)(rows_valid * sizeof(cplx))) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // sC has been read
+                __syncwarp();
+                if (lane == 0) mbar_arrive(cempty);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");               // all writes performed
+            return;
+        }
         if (warp != NCONS) return;
         long long it = 0, ib = 0;
         const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
@@ -330,13 +363,6 @@ __global__ void __launch_bounds__(m3::NTHREADS, 1) zgemm3m_dmma_kernel(ZgemmPara
             const cplx* A = p.A + (long long)bz * p.strideA;
             const cplx* B = p.B + (long long)bz * p.strideB;
             const int rows_valid = min(TM, p.M - m0), cols_valid = min(TN, p.N - n0);
-            if (p.beta) {
-                // warm L2 with THIS tile's C: the consumers add it in their epilogue, about one tile time from now
-                const cplx* C2 = p.C + (long long)bz * p.strideC + m0 + (long long)n0 * p.ldc;
-                for (int j = lane; j < cols_valid; j += 32)
-                    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(C2 + (long long)j * p.ldc),
-                                 "r"((uint32_t)(rows_valid * sizeof(cplx))), "l"(stream) : "memory");
-            }
             for (int kt = 0; kt < KT; ++kt, ++it) {
                 if (kt % APB == 0) {
                     const int sb = (int)(ib % BSTAGES), kb0 = kt * KC;
@@ -369,12 +395,8 @@ __global__ void __launch_bounds__(m3::NTHREADS, 1) zgemm3m_dmma_kernel(ZgemmPara
     const long long sflip = (p.negate ? 1LL : 0LL) << 63;
     const int arow = wm * (8 * QA) + g;
     const int bcol = wn * (8 * QB) + g;
-    long long it = 0, ib = 0;
-    const uint64_t stream = l2_policy_evict_first();
+    long long it = 0, ib = 0, tl = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int mt = (int)(tile % tiles_m), nt = (int)((tile / tiles_m) % tiles_n), bz = (int)(tile / ((long long)tiles_m * tiles_n));
-        const int m0 = mt * TM, n0 = nt * TN;
-        cplx* C = p.C + (long long)bz * p.strideC;
         double p1[QA][QB][2], p2[QA][QB][2], p3[QA][QB][2];
 #pragma unroll
         for (int qa = 0; qa < QA; ++qa)
@@ -382,106 +404,121 @@ __global__ void __launch_bounds__(m3::NTHREADS, 1) zgemm3m_dmma_kernel(ZgemmPara
             for (int qb = 0; qb < QB; ++qb)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) { p1[qa][qb][j] = 0.0; p2[qa][qb][j] = 0.0; p3[qa][qb][j] = 0.0; }
-        const double2* b_s = nullptr;
-        int sb = 0;
-        for (int kt = 0; kt < KT; ++kt, ++it) {
+        // K loop.  The fragments of a k4 step (4 + 3 LDS.128) are loaded one step ahead of the 36 DMMAs that use them, also
+        // ACROSS slab boundaries: the last step of a slab first waits for the next slab's barrier and loads its first
+        // fragments, then issues its own DMMAs and only then releases its slab -- no LDS / barrier latency is exposed
+        // between slabs (needs >= 2 stages of A and of B).
+        struct Frag { double2 a[QA]; double2 b[QB]; };
+        const double2 *a_s = nullptr, *b_sk = nullptr;      // current A slab; current B slab advanced to this A slab's k offset
+        int s = 0, sb = 0;
+        auto enter_slab = [&](int kt) {
             if (kt % APB == 0) {
                 sb = (int)(ib % BSTAGES);
                 mbar_wait(&bfull[sb], (uint32_t)((ib / BSTAGES) & 1));
-                b_s = reinterpret_cast<const double2*>(sB + sb * B_STAGE);
                 ++ib;
             }
-            const int s = (int)(it % STAGES);
-            const int kv = min(KC, p.K - kt * KC);
-            const int kboff = (kt % APB) * KC;
+            s = (int)(it % STAGES);
             mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
-            const double2* a_s = reinterpret_cast<const double2*>(sA + s * A_STAGE);
+            ++it;
+            a_s = reinterpret_cast<const double2*>(sA + s * A_STAGE);
+            b_sk = reinterpret_cast<const double2*>(sB + sb * B_STAGE) + (kt % APB) * KC;
+        };
+        auto load_frag = [&](Frag& f, int ks) {
+            const int kc = 4 * ks + t;                       // this lane's complex k of the k4 step
+#pragma unroll
+            for (int qb = 0; qb < QB; ++qb) f.b[qb] = b_sk[(bcol + 8 * qb) * LDSB + kc];
+#pragma unroll
+            for (int qa = 0; qa < QA; ++qa) f.a[qa] = a_s[kc * LDSA + arow + 8 * qa];
+        };
+        auto mma_frag = [&](const Frag& f) {
+            double br[QB], bi[QB], bs[QB];
+#pragma unroll
+            for (int qb = 0; qb < QB; ++qb) {
+                br[qb] = __longlong_as_double(__double_as_longlong(f.b[qb].x) ^ sflip);
+                bi[qb] = __longlong_as_double(__double_as_longlong(f.b[qb].y) ^ sflip);
+                bs[qb] = br[qb] + bi[qb];
+            }
+#pragma unroll
+            for (int qa = 0; qa < QA; ++qa) {
+                const double as = f.a[qa].x + f.a[qa].y;
+#pragma unroll
+                for (int qb = 0; qb < QB; ++qb) {
+                    dmma884(p1[qa][qb][0], p1[qa][qb][1], f.a[qa].x, br[qb]);
+                    dmma884(p2[qa][qb][0], p2[qa][qb][1], f.a[qa].y, bi[qb]);
+                    dmma884(p3[qa][qb][0], p3[qa][qb][1], as, bs[qb]);
+                }
+            }
+        };
+        auto release_slab = [&](int s_rel, int sb_rel, bool rel_b) {
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[s_rel]);
+                if (rel_b) mbar_arrive(&bempty[sb_rel]);
+            }
+        };
+        constexpr int NS = KC / 4;                           // k4 steps per full slab (even)
+        static_assert(NS % 2 == 0, "fragment ping-pong needs an even number of steps per slab");
+        Frag f0, f1;
+        if (KT > 0) {
+            enter_slab(0);
+            if (p.K >= KC) load_frag(f0, 0);
+        }
+        for (int kt = 0; kt < KT; ++kt) {
+            const int kv = min(KC, p.K - kt * KC);
+            const bool rel_b = (kt % APB == APB - 1 || kt == KT - 1);
             if (kv == KC) {
+                // full slab: f0 holds step 0 (loaded by the previous slab's last step or before the loop)
 #pragma unroll
-                for (int ks = 0; ks < KC / 4; ++ks) {
-                    const int kc = 4 * ks + t;          // this lane's complex k of the k4 step
-                    double br[QB], bi[QB], bs[QB];
-#pragma unroll
-                    for (int qb = 0; qb < QB; ++qb) {
-                        const double2 b = b_s[(bcol + 8 * qb) * LDSB + kboff + kc];
-                        br[qb] = __longlong_as_double(__double_as_longlong(b.x) ^ sflip);
-                        bi[qb] = __longlong_as_double(__double_as_longlong(b.y) ^ sflip);
-                        bs[qb] = br[qb] + bi[qb];
-                    }
-#pragma unroll
-                    for (int qa = 0; qa < QA; ++qa) {
-                        const double2 a = a_s[kc * LDSA + arow + 8 * qa];
-                        const double as = a.x + a.y;
-#pragma unroll
-                        for (int qb = 0; qb < QB; ++qb) {
-                            dmma884(p1[qa][qb][0], p1[qa][qb][1], a.x, br[qb]);
-                            dmma884(p2[qa][qb][0], p2[qa][qb][1], a.y, bi[qb]);
-                            dmma884(p3[qa][qb][0], p3[qa][qb][1], as, bs[qb]);
+                for (int ks = 0; ks < NS; ks += 2) {
+                    load_frag(f1, ks + 1);
+                    mma_frag(f0);
+                    if (ks + 2 < NS) {
+                        load_frag(f0, ks + 2);
+                        mma_frag(f1);
+                    } else {
+                        const int s_rel = s, sb_rel = sb;
+                        if (kt + 1 < KT) {
+                            enter_slab(kt + 1);
+                            if (p.K - (kt + 1) * KC >= KC) load_frag(f0, 0);
                         }
+                        mma_frag(f1);
+                        release_slab(s_rel, sb_rel, rel_b);
                     }
                 }
             } else {
-                // K tail: complex k >= kv contribute exact zeros (both fragments are cleared in registers)
+                // K tail (always the last slab of the tile): complex k >= kv contribute exact zeros
                 for (int ks = 0; 4 * ks < kv; ++ks) {
-                    const int kc = 4 * ks + t;
-                    const bool ok = kc < kv;
-                    double br[QB], bi[QB], bs[QB];
+                    const bool ok = 4 * ks + t < kv;
+                    Frag f;
+                    if (ok) load_frag(f, ks);
+                    else {
 #pragma unroll
-                    for (int qb = 0; qb < QB; ++qb) {
-                        const double2 b = ok ? b_s[(bcol + 8 * qb) * LDSB + kboff + kc] : make_double2(0.0, 0.0);
-                        br[qb] = __longlong_as_double(__double_as_longlong(b.x) ^ sflip);
-                        bi[qb] = __longlong_as_double(__double_as_longlong(b.y) ^ sflip);
-                        bs[qb] = br[qb] + bi[qb];
+                        for (int qb = 0; qb < QB; ++qb) f.b[qb] = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int qa = 0; qa < QA; ++qa) f.a[qa] = make_double2(0.0, 0.0);
                     }
-#pragma unroll
-                    for (int qa = 0; qa < QA; ++qa) {
-                        const double2 a = ok ? a_s[kc * LDSA + arow + 8 * qa] : make_double2(0.0, 0.0);
-                        const double as = a.x + a.y;
-#pragma unroll
-                        for (int qb = 0; qb < QB; ++qb) {
-                            dmma884(p1[qa][qb][0], p1[qa][qb][1], a.x, br[qb]);
-                            dmma884(p2[qa][qb][0], p2[qa][qb][1], a.y, bi[qb]);
-                            dmma884(p3[qa][qb][0], p3[qa][qb][1], as, bs[qb]);
-                        }
-                    }
+                    mma_frag(f);
                 }
-            }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&empty[s]);
-                if (kt % APB == APB - 1 || kt == KT - 1) mbar_arrive(&bempty[sb]);
+                release_slab(s, sb, rel_b);
             }
         }
-        // epilogue: Re = P1 - P2, Im = (P3 - P1) - P2, plus C when accumulating (L2 hits: prefetched by the producer).
-        // The C loads of row block qa + 1 are issued before the stores of row block qa, so one L2 latency is exposed per
-        // tile instead of one per row block.
-        const int er = m0 + wm * (8 * QA) + g, ec = n0 + wn * (8 * QB) + 2 * t;
-        cplx cv[2][QB][2];
-        auto load_c = [&](int qa, cplx (&dst)[QB][2]) {
+        // epilogue: Re = P1 - P2, Im = (P3 - P1) - P2 go to the staging tile (fragment order, conflict-free STS.128); the
+        // storer warp adds them to / stores them over C asynchronously while this warp starts the next tile
+        if (tl >= 1) mbar_wait(cempty, (uint32_t)((tl - 1) & 1));
+        {
+            cplx* dst = sC + (wn * (8 * QB) + 2 * t) * LDSC + wm * (8 * QA) + g;
 #pragma unroll
-            for (int qb = 0; qb < QB; ++qb)
+            for (int qa = 0; qa < QA; ++qa)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int r = er + 8 * qa, c = ec + 8 * qb + j;
-                    dst[qb][j] = (p.beta && r < p.M && c < p.N) ? ld_stream(&C[r + (long long)c * p.ldc], stream) : cmake(0.0, 0.0);
-                }
-        };
-        load_c(0, cv[0]);
+                for (int qb = 0; qb < QB; ++qb)
 #pragma unroll
-        for (int qa = 0; qa < QA; ++qa) {
-            if (qa + 1 < QA) load_c(qa + 1, cv[(qa + 1) & 1]);
-#pragma unroll
-            for (int qb = 0; qb < QB; ++qb)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int r = er + 8 * qa, c = ec + 8 * qb + j;
-                    if (r < p.M && c < p.N) {
-                        const double re = (p1[qa][qb][j] - p2[qa][qb][j]) + cv[qa & 1][qb][j].x;
-                        const double im = ((p3[qa][qb][j] - p1[qa][qb][j]) - p2[qa][qb][j]) + cv[qa & 1][qb][j].y;
-                        st_stream(&C[r + (long long)c * p.ldc], cmake(re, im), stream);
-                    }
-                }
+                    for (int j = 0; j < 2; ++j)
+                        dst[(8 * qb + j) * LDSC + 8 * qa] = cmake(p1[qa][qb][j] - p2[qa][qb][j], (p3[qa][qb][j] - p1[qa][qb][j]) - p2[qa][qb][j]);
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk (async proxy) reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cfull);
+        ++tl;
     }
 }
 
@@ -551,12 +588,9 @@ static cudaError_t launch_3m(const ZgemmParams& p, cudaStream_t stream) {
     static int cfg = -1;
     if (cfg < 0) { const char* e = getenv("MAUS_3M_CFG"); cfg = e ? atoi(e) : 0; }
     switch (cfg) {
-        case 1: return launch_3m_cfg<m3::Pipe<16, 4, 32, 2>>(p, stream);
-        case 2: return launch_3m_cfg<m3::Pipe<16, 3, 64, 2>>(p, stream);
-        case 3: return launch_3m_cfg<m3::Pipe<32, 2, 32, 2>>(p, stream);
-        case 4: return launch_3m_cfg<m3::Pipe<32, 2, 32, 3>>(p, stream);
-        case 5: return launch_3m_cfg<m3::Pipe<16, 3, 32, 2>>(p, stream);
-        default: return launch_3m_cfg<m3::Pipe<32, 2, 32, 3>>(p, stream);     // measured best (profiles/README_r01.md)
+        case 1: return launch_3m_cfg<m3::Pipe<8, 4, 32, 2>>(p, stream);
+        case 2: return launch_3m_cfg<m3::Pipe<8, 4, 16, 4>>(p, stream);
+        default: return launch_3m_cfg<m3::Pipe<16, 2, 32, 2>>(p, stream);
     }
 }
 
