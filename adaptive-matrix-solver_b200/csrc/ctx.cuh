@@ -27,9 +27,9 @@ struct ProfAccum {
     std::vector<int> kind;           // MAUS_PROF_* (include/maus_b200.h)
     std::vector<long long> tag;      // optional per-launch tag (GEMM shape), printed when MAUS_GEMM_LOG is set
     size_t used = 0;
-    double ms[8] = {0};
-    long long launches[8] = {0};
-    double work[8] = {0};            // flops (GEMM kinds) / bytes (HBM kinds)
+    double ms[MAUS_PROF_KINDS] = {0};
+    long long launches[MAUS_PROF_KINDS] = {0};
+    double work[MAUS_PROF_KINDS] = {0};            // flops (GEMM kinds) / bytes (HBM kinds)
 };
 
 struct maus_ctx {
@@ -48,6 +48,7 @@ struct maus_ctx {
     cplx *V = nullptr, *X = nullptr, *Y = nullptr;
     cplx *lambda = nullptr, *sigma = nullptr;
     double *psi = nullptr, *alpha = nullptr, *vnorm2 = nullptr, *resid = nullptr, *mixnorm = nullptr;
+    double* vscratch = nullptr;    // per-block partials of the multi-block vector reductions (vec.cu, long vectors)
     unsigned long long* keys = nullptr;
     int *status = nullptr, *iters = nullptr, *info = nullptr;
     unsigned char *skip = nullptr, *jac = nullptr;

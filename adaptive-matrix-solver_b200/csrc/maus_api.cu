@@ -88,7 +88,8 @@ static void free_population(maus_ctx* ctx) {
     maus_dev_free(ctx, ctx->Y, n * C * sizeof(cplx));
     maus_dev_free(ctx, ctx->lambda, C * sizeof(cplx)); maus_dev_free(ctx, ctx->sigma, C * sizeof(cplx));
     maus_dev_free(ctx, ctx->psi, C * 8); maus_dev_free(ctx, ctx->alpha, C * 8); maus_dev_free(ctx, ctx->vnorm2, C * 8);
-    maus_dev_free(ctx, ctx->resid, C * 8); maus_dev_free(ctx, ctx->mixnorm, C * 8); maus_dev_free(ctx, ctx->keys, C * 8);
+    maus_dev_free(ctx, ctx->resid, C * 8); maus_dev_free(ctx, ctx->mixnorm, C * 8);
+    maus_dev_free(ctx, ctx->vscratch, vec_scratch_doubles(C) * 8); ctx->vscratch = nullptr; maus_dev_free(ctx, ctx->keys, C * 8);
     maus_dev_free(ctx, ctx->status, C * 4); maus_dev_free(ctx, ctx->iters, C * 4); maus_dev_free(ctx, ctx->info, C * 4);
     maus_dev_free(ctx, ctx->skip, C); maus_dev_free(ctx, ctx->jac, C);
     ctx->V = ctx->X = ctx->Y = nullptr; ctx->lambda = ctx->sigma = nullptr;
@@ -123,6 +124,7 @@ int maus_ensure_population(maus_ctx* ctx, long long C) {
     if ((rc = ensure(ctx, &ctx->vnorm2, cap))) return rc;
     if ((rc = ensure(ctx, &ctx->resid, cap))) return rc;
     if ((rc = ensure(ctx, &ctx->mixnorm, cap))) return rc;
+    if ((rc = ensure(ctx, &ctx->vscratch, (long long)vec_scratch_doubles(cap)))) return rc;
     if ((rc = ensure(ctx, &ctx->keys, cap))) return rc;
     if ((rc = ensure(ctx, &ctx->status, cap))) return rc;
     if ((rc = ensure(ctx, &ctx->iters, cap))) return rc;
@@ -232,7 +234,7 @@ extern "C" int maus_profile_reset(maus_ctx* ctx, int enable) {
     ProfAccum& pr = ctx->prof;
     pr.enabled = enable != 0;
     pr.used = 0;
-    for (int k = 0; k < 8; ++k) { pr.ms[k] = 0.0; pr.launches[k] = 0; pr.work[k] = 0.0; }
+    for (int k = 0; k < MAUS_PROF_KINDS; ++k) { pr.ms[k] = 0.0; pr.launches[k] = 0; pr.work[k] = 0.0; }
     return MAUS_OK;
 }
 
@@ -252,7 +254,7 @@ extern "C" int maus_profile_read(maus_ctx* ctx, double* lu_gemm_ms, int64_t* lu_
 }
 
 extern "C" int maus_profile_read_kind(maus_ctx* ctx, int kind, double* ms, int64_t* launches, double* work) {
-    if (!ctx || kind < 0 || kind >= 8) return MAUS_E_ARG;
+    if (!ctx || kind < 0 || kind >= MAUS_PROF_KINDS) return MAUS_E_ARG;
     int rc = maus_profile_read(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc) return rc;
     if (ms) *ms = ctx->prof.ms[kind];
@@ -582,7 +584,9 @@ extern "C" int maus_rq(maus_ctx* ctx, int64_t C, const double* V, double* lambda
     cudaStream_t st = ctx->stream;
     if (V) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->V, V, (size_t)C * n * sizeof(cplx), cudaMemcpyHostToDevice, st));
     if ((rc = maus_apply_matrix(ctx, 0, ctx->V, n, ctx->Y, n, C))) return rc;
-    MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, nullptr, st));
+    { int hv = prof_begin(ctx, MAUS_PROF_VEC, 32.0 * n * (double)C);
+    MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, nullptr, ctx->vscratch, st));
+      prof_end(ctx, hv); }
     ctx->launches += 1;
     if (lambda_out) MAUS_CUDA(ctx, cudaMemcpyAsync(lambda_out, ctx->lambda, (size_t)C * sizeof(cplx), cudaMemcpyDeviceToHost, st));
     if (vnorm2_out) MAUS_CUDA(ctx, cudaMemcpyAsync(vnorm2_out, ctx->vnorm2, (size_t)C * 8, cudaMemcpyDeviceToHost, st));
@@ -671,8 +675,10 @@ extern "C" int maus_solve_with_R(maus_ctx* ctx, const double* sigma, const doubl
 static int residual_device(maus_ctx* ctx, long long C, int problem_type, int res_slot) {
     int rc = maus_apply_matrix(ctx, res_slot, ctx->V, ctx->n, ctx->Y, ctx->n, C); if (rc) return rc;
     if (problem_type == MAUS_SOLVE_LINEAR_SYSTEM && !ctx->b_set) return maus_fail(ctx, MAUS_E_STATE, "rhs not set");
+    { int hv = prof_begin(ctx, MAUS_PROF_VEC, 32.0 * ctx->n * (double)C);
     MAUS_CUDA(ctx, vec_residual_finish(ctx->V, ctx->Y, (int)ctx->n, (int)C, problem_type, ctx->lambda, ctx->b, ctx->resid,
-                                       ctx->stream));
+                                       ctx->vscratch, ctx->stream));
+      prof_end(ctx, hv); }
     ctx->launches += 2;
     return MAUS_OK;
 }
@@ -695,7 +701,9 @@ extern "C" int maus_mix_residual(maus_ctx* ctx, int64_t C, int problem_type, con
     } else {
         MAUS_CUDA(ctx, cudaMemsetAsync(ctx->status, 0, (size_t)C * 4, st));
     }
-    MAUS_CUDA(ctx, vec_mix_normalise(ctx->V, ctx->X, (int)n, (int)C, problem_type, ctx->alpha, ctx->mixnorm, ctx->status, st));
+    { int hv = prof_begin(ctx, MAUS_PROF_VEC, (problem_type == MAUS_EIGENVALUE ? 80.0 : 48.0) * n * (double)C)   /* eigen: second pass normalises */;
+    MAUS_CUDA(ctx, vec_mix_normalise(ctx->V, ctx->X, (int)n, (int)C, problem_type, ctx->alpha, ctx->mixnorm, ctx->status, ctx->vscratch, st));
+      prof_end(ctx, hv); }
     ctx->launches += 1;
     if ((rc = residual_device(ctx, C, problem_type, res_slot))) return rc;
     if (V_out) MAUS_CUDA(ctx, cudaMemcpyAsync(V_out, ctx->V, (size_t)C * n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
@@ -749,7 +757,9 @@ extern "C" int maus_step(maus_ctx* ctx, int64_t C, int problem_type, int method,
     if (problem_type == MAUS_EIGENVALUE) {
         // AMS:264-270: lambda = RQ(v); sigma = lambda
         if ((rc = maus_apply_matrix(ctx, 0, ctx->V, n, ctx->Y, n, C))) return rc;
-        MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, ctx->status, st));
+        { int hv = prof_begin(ctx, MAUS_PROF_VEC, 32.0 * n * (double)C);
+        MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, ctx->status, ctx->vscratch, st));
+          prof_end(ctx, hv); }
         ctx->launches += 1;
         MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->sigma, ctx->lambda, (size_t)C * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
         rhs = ctx->V; rstride = n;
@@ -764,7 +774,9 @@ extern "C" int maus_step(maus_ctx* ctx, int64_t C, int problem_type, int method,
         for (long long c = 0; c < C; ++c) max_psi = std::max(max_psi, std::fabs(psi[c]));
         if ((rc = solve_device(ctx, C, method, rhs, rstride, nullptr, rng_key != nullptr, max_psi))) return rc;
     }
-    MAUS_CUDA(ctx, vec_mix_normalise(ctx->V, ctx->X, (int)n, (int)C, problem_type, ctx->alpha, ctx->mixnorm, ctx->status, st));
+    { int hv = prof_begin(ctx, MAUS_PROF_VEC, (problem_type == MAUS_EIGENVALUE ? 80.0 : 48.0) * n * (double)C)   /* eigen: second pass normalises */;
+    MAUS_CUDA(ctx, vec_mix_normalise(ctx->V, ctx->X, (int)n, (int)C, problem_type, ctx->alpha, ctx->mixnorm, ctx->status, ctx->vscratch, st));
+      prof_end(ctx, hv); }
     ctx->launches += 1;
     if ((rc = residual_device(ctx, C, problem_type, res_slot))) return rc;
     if (V_io) MAUS_CUDA(ctx, cudaMemcpyAsync(V_io, ctx->V, (size_t)C * n * sizeof(cplx), cudaMemcpyDeviceToHost, st));

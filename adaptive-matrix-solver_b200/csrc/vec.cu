@@ -232,6 +232,216 @@ __global__ void __launch_bounds__(256) diag_amax_kernel(const cplx* __restrict__
         atomicMax(reinterpret_cast<unsigned long long*>(amax), (unsigned long long)__double_as_longlong(m));   // m >= 0: bit order = value order
 }
 
+// ---- multi-block variants for long vectors (n >= VMB_MIN_N: the sparse configurations, n ~ 1e6) ------------------------------
+// One CTA per candidate cannot stream a 16 MB vector at HBM speed.  Here a candidate's vector is split over up to VMB_MAXBLK
+// CTAs; every pass leaves per-block partials in `scratch` ([C][VMB_MAXBLK][4] doubles) and the consumer re-reduces them in a
+// FIXED order, so the results do not depend on scheduling.  Same formulas (scaled 2-norms, thresholds) as the one-CTA kernels.
+constexpr int VMB_MAXBLK = 64, VMB_MIN_N = 32768;
+__device__ __forceinline__ void vmb_range(int n, int nblk, int blk, int& i0, int& i1) {
+    const int per = ((n + nblk - 1) / nblk + 1) & ~1;
+    i0 = min(n, blk * per);
+    i1 = min(n, i0 + per);
+}
+__device__ __forceinline__ double vmb_sum(const double* part, int nblk, int k) {
+    double s = 0.0;
+    for (int q = 0; q < nblk; ++q) s += part[q * 4 + k];
+    return s;
+}
+__device__ __forceinline__ double vmb_max(const double* part, int nblk, int k) {
+    double s = 0.0;
+    for (int q = 0; q < nblk; ++q) s = fmax(s, part[q * 4 + k]);
+    return s;
+}
+
+// The 2-norms are accumulated UNSCALED in the same pass that finds max |component|; the scaled (dznrm2-like, overflow-safe)
+// sum of the one-CTA kernels is only recomputed when the plain sum left the safe range (never for normalised vectors).
+__device__ __forceinline__ bool vmb_ss_safe(double ss) { return isfinite(ss) && ss > 1e-290; }
+
+__global__ void __launch_bounds__(RED_NT) rq_part_kernel(const cplx* __restrict__ V, const cplx* __restrict__ Y, int n, double* scratch) {
+    __shared__ double sh[RED_NT / 32];
+    const int c = blockIdx.y;
+    int i0, i1; vmb_range(n, gridDim.x, blockIdx.x, i0, i1);
+    const cplx* v = V + (long long)c * n;
+    const cplx* y = Y + (long long)c * n;
+    double nr = 0.0, ni = 0.0, d = 0.0;
+    for (int i = i0 + threadIdx.x; i < i1; i += 4 * RED_NT) {
+        cplx a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = i + u * RED_NT;
+            a[u] = (k < i1) ? __ldcs(&v[k]) : cmake(0.0, 0.0);
+            b[u] = (k < i1) ? __ldcs(&y[k]) : cmake(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            nr = fma(a[u].x, b[u].x, nr); nr = fma(a[u].y, b[u].y, nr);     // conj(a) * b
+            ni = fma(a[u].x, b[u].y, ni); ni = fma(-a[u].y, b[u].x, ni);
+            d = fma(a[u].x, a[u].x, d); d = fma(a[u].y, a[u].y, d);
+        }
+    }
+    nr = block_sum(nr, sh); ni = block_sum(ni, sh); d = block_sum(d, sh);
+    if (threadIdx.x == 0) {
+        double* o = scratch + ((long long)c * VMB_MAXBLK + blockIdx.x) * 4;
+        o[0] = nr; o[1] = ni; o[2] = d;
+    }
+}
+__global__ void rq_final_kernel(const double* __restrict__ scratch, int nblk, int C, cplx* lambda, double* vnorm2, int* status) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double* part = scratch + (long long)c * VMB_MAXBLK * 4;
+    const double nr = vmb_sum(part, nblk, 0), ni = vmb_sum(part, nblk, 1), d = vmb_sum(part, nblk, 2);
+    vnorm2[c] = d;
+    lambda[c] = (fabs(d) < 1e-12) ? cmake(0.0, 0.0) : cmake(nr / d, ni / d);     // AMS:265-268
+    if (status && sqrt(d) < 1e-10) status[c] = MAUS_ST_V_COLLAPSED;              // AMS:259
+}
+
+// pass 1: v <- (1-a) v + a x; per block: max |component| -> part[0], plain sum of squares -> part[1]
+__global__ void __launch_bounds__(RED_NT) mix_part_kernel(cplx* __restrict__ V, const cplx* __restrict__ X, int n,
+                                                          const double* __restrict__ alpha, const int* __restrict__ status,
+                                                          double* scratch) {
+    __shared__ double sh[RED_NT / 32];
+    const int c = blockIdx.y;
+    if (status[c] != 0) return;
+    int i0, i1; vmb_range(n, gridDim.x, blockIdx.x, i0, i1);
+    cplx* v = V + (long long)c * n;
+    const cplx* x = X + (long long)c * n;
+    const double a = alpha[c], oma = 1.0 - a;
+    double amax = 0.0, ss = 0.0;
+    for (int i = i0 + threadIdx.x; i < i1; i += 4 * RED_NT) {
+        cplx vi[4], xi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = i + u * RED_NT;
+            vi[u] = (k < i1) ? v[k] : cmake(0.0, 0.0);
+            xi[u] = (k < i1) ? __ldcs(&x[k]) : cmake(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = i + u * RED_NT;
+            const cplx m = cmake(oma * vi[u].x + a * xi[u].x, oma * vi[u].y + a * xi[u].y);
+            if (k < i1) v[k] = m;
+            amax = fmax(amax, fmax(fabs(m.x), fabs(m.y)));
+            ss = fma(m.x, m.x, ss); ss = fma(m.y, m.y, ss);
+        }
+    }
+    amax = block_max(amax, sh); ss = block_sum(ss, sh);
+    if (threadIdx.x == 0) {
+        double* o = scratch + ((long long)c * VMB_MAXBLK + blockIdx.x) * 4;
+        o[0] = amax; o[1] = ss;
+    }
+}
+// scaled 2-norm of a whole vector by ONE block (rare fallback when the plain sum of squares over- / underflowed)
+__device__ double vmb_scaled_norm_slow(const cplx* __restrict__ v, int n, double amax, double* sh) {
+    const double inv = 1.0 / amax;
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < n; i += RED_NT) {
+        const cplx m = v[i];
+        const double p = m.x * inv, q = m.y * inv;
+        ss = fma(p, p, ss); ss = fma(q, q, ss);
+    }
+    ss = block_sum(ss, sh);
+    return amax * sqrt(ss);
+}
+// pass 2: norm from the partials, normalisation (eigen) / collapse status.  Skipped candidates are recognised by the
+// preset part[0] = -1 (status[c] itself is updated by block 0 while other blocks of this pass may still be starting).
+__global__ void __launch_bounds__(RED_NT) mix_apply_kernel(cplx* __restrict__ V, int n, int problem_type, double* mixnorm,
+                                                           int* status, const double* __restrict__ scratch) {
+    __shared__ double sh[RED_NT / 32];
+    const int c = blockIdx.y;
+    const double* part = scratch + (long long)c * VMB_MAXBLK * 4;
+    if (part[0] < 0.0) { if (blockIdx.x == 0 && threadIdx.x == 0 && mixnorm) mixnorm[c] = 0.0; return; }
+    int i0, i1; vmb_range(n, gridDim.x, blockIdx.x, i0, i1);
+    cplx* v = V + (long long)c * n;
+    const double amax = vmb_max(part, gridDim.x, 0);
+    const double ss = vmb_sum(part, gridDim.x, 1);
+    double nv;
+    if (!(amax > 0.0) || !isfinite(amax)) nv = amax;
+    else if (vmb_ss_safe(ss)) nv = sqrt(ss);
+    else nv = vmb_scaled_norm_slow(v, n, amax, sh);          // every block recomputes the same value
+    if (blockIdx.x == 0 && threadIdx.x == 0 && mixnorm) mixnorm[c] = nv;
+    if (problem_type == MAUS_EIGENVALUE) {
+        if (nv > 1e-10) {                                    // AMS:282
+            for (int i = i0 + threadIdx.x; i < i1; i += RED_NT) { cplx m = v[i]; v[i] = cmake(m.x / nv, m.y / nv); }
+        } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+            status[c] = MAUS_ST_MIX_COLLAPSED;               // AMS:283
+        }
+    }
+}
+__global__ void mix_preset_kernel(const int* __restrict__ status, int C, double* scratch) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) scratch[(long long)c * VMB_MAXBLK * 4] = (status[c] != 0) ? -1.0 : 0.0;
+}
+
+// residual, one pass: r = y - lambda v (eigen) / y - b (linear); max |component|, plain sum of squares, NaN flag of y and v
+__global__ void __launch_bounds__(RED_NT) res_part_kernel(const cplx* __restrict__ V, const cplx* __restrict__ Y, int n, int problem_type,
+                                                          const cplx* __restrict__ lambda, const cplx* __restrict__ b, double* scratch) {
+    __shared__ double sh[RED_NT / 32];
+    const int c = blockIdx.y;
+    int i0, i1; vmb_range(n, gridDim.x, blockIdx.x, i0, i1);
+    const cplx* v = V + (long long)c * n;
+    const cplx* y = Y + (long long)c * n;
+    const bool eig = problem_type == MAUS_EIGENVALUE;
+    const cplx lam = eig ? lambda[c] : cmake(0.0, 0.0);
+    double amax = 0.0, ss = 0.0, bad = 0.0;
+    for (int i = i0 + threadIdx.x; i < i1; i += 4 * RED_NT) {
+        cplx r[4], w[4], bb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = i + u * RED_NT;
+            r[u] = (k < i1) ? __ldcs(&y[k]) : cmake(0.0, 0.0);
+            w[u] = (k < i1) ? v[k] : cmake(0.0, 0.0);
+            bb[u] = (!eig && k < i1) ? b[k] : cmake(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (r[u].x != r[u].x || r[u].y != r[u].y || w[u].x != w[u].x || w[u].y != w[u].y) bad = 1.0;
+            if (eig) cfms(r[u], lam, w[u]); else r[u] = csub(r[u], bb[u]);
+            amax = fmax(amax, fmax(fabs(r[u].x), fabs(r[u].y)));
+            ss = fma(r[u].x, r[u].x, ss); ss = fma(r[u].y, r[u].y, ss);
+        }
+    }
+    amax = block_max(amax, sh); ss = block_sum(ss, sh); bad = block_max(bad, sh);
+    if (threadIdx.x == 0) {
+        double* o = scratch + ((long long)c * VMB_MAXBLK + blockIdx.x) * 4;
+        o[0] = amax; o[1] = ss; o[3] = bad;
+    }
+}
+__global__ void __launch_bounds__(RED_NT) res_final_kernel(const cplx* __restrict__ V, const cplx* __restrict__ Y, int n, int problem_type,
+                                                           const cplx* __restrict__ lambda, const cplx* __restrict__ b,
+                                                           const double* __restrict__ scratch, int nblk, double* resid) {
+    __shared__ double sh[RED_NT / 32];
+    const int c = blockIdx.x;
+    const double* part = scratch + (long long)c * VMB_MAXBLK * 4;
+    const double amax = vmb_max(part, nblk, 0), ss = vmb_sum(part, nblk, 1), bad = vmb_max(part, nblk, 3);
+    double out;
+    if (bad > 0.0) out = nan("");                            // np.linalg.norm propagates NaN (fmax would drop it)
+    else if (!(amax > 0.0) || !isfinite(amax)) out = amax;
+    else if (vmb_ss_safe(ss)) out = sqrt(ss);
+    else {
+        // rare: recompute with the scaled sum (this block alone walks the vector)
+        const cplx* v = V + (long long)c * n;
+        const cplx* y = Y + (long long)c * n;
+        const bool eig = problem_type == MAUS_EIGENVALUE;
+        const cplx lam = eig ? lambda[c] : cmake(0.0, 0.0);
+        const double inv = 1.0 / amax;
+        double s2 = 0.0;
+        for (int i = threadIdx.x; i < n; i += RED_NT) {
+            cplx r = y[i];
+            if (eig) cfms(r, lam, v[i]); else r = csub(r, b[i]);
+            const double p = r.x * inv, q = r.y * inv;
+            s2 = fma(p, p, s2); s2 = fma(q, q, s2);
+        }
+        s2 = block_sum(s2, sh);
+        out = amax * sqrt(s2);
+    }
+    if (threadIdx.x == 0) resid[c] = out;
+}
+
+__host__ inline int vmb_blocks(int n) {
+    const int want = (n + RED_NT * 8 - 1) / (RED_NT * 8);      // >= 8 elements per thread
+    return want < 1 ? 1 : (want > VMB_MAXBLK ? VMB_MAXBLK : want);
+}
+
 }  // namespace
 
 cudaError_t vec_diag_amax(const cplx* A_rm, int n, cplx* diag, double* amax, cudaStream_t stream) {
@@ -245,23 +455,44 @@ cudaError_t vec_rowmajor_to_colmajor(const cplx* in_rm, cplx* out_cm, int n, cud
     return cudaGetLastError();
 }
 
+size_t vec_scratch_doubles(long long C) { return (size_t)C * VMB_MAXBLK * 4; }
+
 cudaError_t vec_rq_finish(const cplx* V, const cplx* Y, int n, int C, cplx* lambda, double* vnorm2, int* status,
-                          cudaStream_t stream) {
+                          double* scratch, cudaStream_t stream) {
     if (C <= 0) return cudaSuccess;
+    if (scratch && n >= VMB_MIN_N) {
+        const int nblk = vmb_blocks(n);
+        rq_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, scratch);
+        rq_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(scratch, nblk, C, lambda, vnorm2, status);
+        return cudaGetLastError();
+    }
     rq_finish_kernel<<<C, RED_NT, 0, stream>>>(V, Y, n, lambda, vnorm2, status);
     return cudaGetLastError();
 }
 
 cudaError_t vec_mix_normalise(cplx* V, const cplx* X, int n, int C, int problem_type, const double* alpha,
-                              double* mixnorm, int* status, cudaStream_t stream) {
+                              double* mixnorm, int* status, double* scratch, cudaStream_t stream) {
     if (C <= 0) return cudaSuccess;
+    if (scratch && n >= VMB_MIN_N) {
+        const int nblk = vmb_blocks(n);
+        mix_preset_kernel<<<(C + 127) / 128, 128, 0, stream>>>(status, C, scratch);
+        mix_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, X, n, alpha, status, scratch);
+        mix_apply_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, n, problem_type, mixnorm, status, scratch);
+        return cudaGetLastError();
+    }
     mix_normalise_kernel<<<C, RED_NT, 0, stream>>>(V, X, n, problem_type, alpha, mixnorm, status);
     return cudaGetLastError();
 }
 
 cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda,
-                                const cplx* b, double* resid, cudaStream_t stream) {
+                                const cplx* b, double* resid, double* scratch, cudaStream_t stream) {
     if (C <= 0) return cudaSuccess;
+    if (scratch && n >= VMB_MIN_N) {
+        const int nblk = vmb_blocks(n);
+        res_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch);
+        res_final_kernel<<<C, RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch, nblk, resid);
+        return cudaGetLastError();
+    }
     residual_finish_kernel<<<C, RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, resid);
     nan_scan_kernel<<<C, RED_NT, 0, stream>>>(Y, V, n, resid);
     return cudaGetLastError();

@@ -106,7 +106,7 @@ class MausEngine:
         return dict(lu_gemm_ms=a.value, lu_gemm_launches=b.value, lu_gemm_flops=c.value, matvec_ms=d.value,
                     matvec_launches=e.value, matvec_bytes=f.value)
 
-    PROF_KINDS = ("lu_gemm", "matvec", "panel", "trtri", "backsolve", "build", "permute", "matvec_gemm")
+    PROF_KINDS = ("lu_gemm", "matvec", "panel", "trtri", "backsolve", "build", "permute", "matvec_gemm", "vec")
 
     def profile_breakdown(self):
         """{kind: dict(ms, launches, work)} accumulated since profile_reset(True)"""

@@ -125,8 +125,10 @@ def lu_gemm_algorithmic(n, cand, nb=128, group=4, leaf=64):
 
 # DRAM traffic of the GEMM launches measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum over the 151 LU launches
 # + 2 batched A*V launches of one generation at n = 4096 with 16 candidates: profiles/launches_r01_final.csv), per candidate
-NCU_GEMM_DRAM_BYTES_PER_CANDIDATE = (33.565e9 + 13.110e9) / 16.0
-NCU_GEMM_TRAFFIC_SOURCE = "profiles/launches_r01_final.csv"
+NCU_GEMM_DRAM_BYTES_PER_CANDIDATE = ((27.326e9 + 12.371e9) / 16.0 if os.environ.get("MAUS_GEMM_3M", "1") != "0"
+                                     else (33.565e9 + 13.110e9) / 16.0)
+NCU_GEMM_TRAFFIC_SOURCE = ("profiles/launches_r01_3m.csv" if os.environ.get("MAUS_GEMM_3M", "1") != "0"
+                           else "profiles/launches_r01_final.csv")
 
 
 def vector_alpha_update(alpha, resid, prev):

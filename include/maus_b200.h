@@ -193,6 +193,8 @@ int maus_profile_read(maus_ctx* ctx, double* lu_gemm_ms, int64_t* lu_gemm_launch
 #define MAUS_PROF_BUILD       5   /* lu_build_aug_kernel (bytes) */
 #define MAUS_PROF_PERMUTE     6
 #define MAUS_PROF_MATVEC_GEMM 7   /* zgemm_dmma_kernel as batched A*V (flops) */
+#define MAUS_PROF_VEC         8   /* rq_finish / mix_normalise / residual_finish families (algorithmic bytes) */
+#define MAUS_PROF_KINDS       9
 int maus_profile_read_kind(maus_ctx* ctx, int kind, double* ms, int64_t* launches, double* work);
 /* the context's CUDA stream as a void* (cudaStream_t) so a host layer can order its own work after it */
 void* maus_stream(maus_ctx* ctx);

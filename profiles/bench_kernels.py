@@ -15,7 +15,7 @@ from adaptive_matrix_solver_b200.workloads import k2_matrix, k4_system, k5_spars
 
 HBM = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) \
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
-sections = set(sys.argv[1:]) or {"gemv", "spmm", "k2", "k4", "k5"}
+sections = set(sys.argv[1:]) or {"gemv", "spmm", "vec", "k2", "k4", "k5"}
 eng = pkg.MausEngine(0)
 
 
@@ -50,6 +50,36 @@ if "spmm" in sections:
     eng.set_matrix(A)
     for C_ in (1, 4):
         matvec_roofline("csr_spmm_kernel", C_, 20, 20.0 * A.nnz + 8.0 * (n + 1) + 32.0 * n * C_)
+
+if "vec" in sections:
+    # fused vector kernels on long vectors (n = 1M, 8 candidates: the K5 shapes), multi-block reductions; algorithmic bytes =
+    # 32 n C (RQ: v, y), 80 n C (mix: read v, x, write v; normalise: read v, write v -- the norm is only known after
+    # the first pass and 16 MB vectors do not stay on chip), 32 n C (residual: v, y)
+    n = 1_000_000
+    if eng.n != n or not eng.is_sparse:
+        eng.set_matrix(k5_sparse(n))
+    for C_ in (8, 32):
+        rng = np.random.default_rng(2)
+        V = rng.random((C_, n)) + 1j * rng.random((C_, n)); V /= np.linalg.norm(V, axis=1, keepdims=True)
+        eng.upload_vectors(V)
+        lam, _ = eng.rq(C_=C_)
+        for name, fn, alg in (("rq_part + rq_final (Rayleigh quotient dots)", lambda: eng.rq(C_=C_), 32.0 * n * C_),
+                              ("res_part + res_final (residual norm, one pass)", lambda: eng.residual(_abi.EIGENVALUE, lam=lam, C_=C_), 32.0 * n * C_),
+                              ("mix_part + mix_apply (mix + normalise)",
+                               lambda: eng.mix_residual(_abi.EIGENVALUE, np.full(C_, 0.5), lambda_old=lam, want_v=False), 80.0 * n * C_)):
+            for _ in range(2):
+                fn()
+            eng.profile_reset(True)
+            reps = 10
+            for _ in range(reps):
+                fn()
+            bd = eng.profile_breakdown()["vec"]; eng.profile_reset(False)
+            calls = reps * (2 if name.startswith("mix") else 1)       # mix_residual also runs the residual family
+            ms = bd["ms"] / reps
+            byts = bd["work"] / reps
+            emit(kernel=name, n=n, candidates=C_, ms_per_call=round(ms, 4), algorithmic_bytes_per_call=byts,
+                 achieved_gbs=round(byts / (ms * 1e-3) / 1e9, 1), hbm_peak_gbs=HBM, frac=round(byts / (ms * 1e-3) / 1e9 / HBM, 3),
+                 note="mix_residual = mix + residual families together" if name.startswith("mix") else None)
 
 if "k2" in sections:
     # config 2: dense non-Hermitian n=1024, 64 candidates, Psi on, 1 GPU: fused generations, resident

@@ -206,3 +206,57 @@ sys.stdout.buffer.write(X.tobytes())
         env = dict(os.environ, MAUS_PHILOX_ALWAYS=flag)
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, check=True).stdout)
     assert len(outs[0]) == 200 * 6 * 16 and outs[0] == outs[1]
+
+
+def test_long_vectors_use_multi_block_reductions(eng):
+    """n >= 32768 (the sparse configurations): Rayleigh quotient, mix + normalise and residual are reduced by many CTAs per
+    candidate with fixed-order partial sums (vec.cu); same formulas as the one-CTA kernels (AMS:264-268, 280-285, 295-299)."""
+    from adaptive_matrix_solver_b200 import _abi
+    from adaptive_matrix_solver_b200.workloads import k5_sparse
+    n, C = 50_001, 3                                   # odd length: ragged last block
+    A = k5_sparse(n, seed=9)
+    rng = np.random.default_rng(12)
+    V = crand(rng, C, n); V /= np.linalg.norm(V, axis=1, keepdims=True)
+    eng.set_matrix(A)
+    X, st, it = eng.solve_shifted(np.zeros(C, dtype=complex), np.zeros(C), rng_key=None, method=_abi.METHOD_GMRES, RHS=V)
+    assert (st == 0).all()
+    eng.upload_vectors(V)
+    lam, vn2 = eng.rq(C_=C)
+    AV = (A @ V.T).T
+    for c in range(C):
+        assert abs(lam[c] - np.vdot(V[c], AV[c]) / np.vdot(V[c], V[c])) <= 1e-13 * abs(lam[c])
+        assert abs(vn2[c] - 1.0) <= 1e-13
+    alpha = np.array([0.3, 0.7, 1.0])
+    Vn, resid, mixn, status = eng.mix_residual(_abi.EIGENVALUE, alpha, lambda_old=lam, skip=[0, 1, 0])
+    for c in (0, 2):
+        m = (1 - alpha[c]) * V[c] + alpha[c] * X[c]
+        nv = np.linalg.norm(m)
+        assert status[c] == 0 and abs(mixn[c] - nv) <= 1e-13 * nv
+        assert np.abs(Vn[c] - m / nv).max() <= 1e-15
+        r = np.linalg.norm(A @ (m / nv) - lam[c] * (m / nv))
+        assert abs(resid[c] - r) <= 1e-12 * max(r, 1.0)
+    assert np.array_equal(Vn[1], V[1]) and mixn[1] == 0.0          # skipped candidate is left untouched
+    # linear system: no normalisation, residual against b
+    b = crand(rng, n)
+    eng.set_rhs(b)
+    eng.solve_shifted(np.zeros(C, dtype=complex), np.zeros(C), rng_key=None, method=_abi.METHOD_GMRES, RHS=V)
+    eng.upload_vectors(V)
+    Vl, resid, mixn, status = eng.mix_residual(_abi.SOLVE_LINEAR_SYSTEM, alpha)
+    for c in range(C):
+        m = (1 - alpha[c]) * V[c] + alpha[c] * X[c]
+        assert np.abs(Vl[c] - m).max() <= 1e-15 * max(1.0, np.abs(m).max())
+        r = np.linalg.norm(A @ m - b)
+        assert abs(resid[c] - r) <= 1e-12 * r
+    # a NaN anywhere surfaces as a NaN residual of that candidate only (np.linalg.norm semantics)
+    Vbad = V.copy(); Vbad[1, n - 2] = np.nan
+    r = eng.residual(_abi.EIGENVALUE, Vbad, lam)
+    assert np.isnan(r[1]) and np.isfinite(r[0]) and np.isfinite(r[2])
+    # entries ~ 1e200: the plain sum of squares overflows, the scaled fallback must return the finite norm
+    Vbig = V.copy(); Vbig[0] *= 1e200
+    r = eng.residual(_abi.EIGENVALUE, Vbig, np.zeros(C, dtype=complex))          # lambda = 0: r = A v
+    ref = np.abs((A @ Vbig[0]) / 1e200)
+    assert np.isfinite(r[0]) and abs(r[0] / 1e200 - np.sqrt((ref ** 2).sum())) <= 1e-12 * np.sqrt((ref ** 2).sum())
+    # collapse: alpha = 1 and x = 0 cannot be produced here, but a zero vector must report V_COLLAPSED-free zero quotient
+    Z = np.zeros((1, n), dtype=np.complex128)
+    lam0, vn20 = eng.rq(Z)
+    assert lam0[0] == 0 and vn20[0] == 0
