@@ -6,9 +6,9 @@ namespace {
 
 // 8 lanes per matrix row (rows have ~20 non-zeros in the K5 workload), 4 rows per warp, CB candidates per pass.
 // Values / column indices are read in contiguous 128 B / 32 B segments per row; candidate entries are gathered.
-constexpr int SP_NT = 256, SP_LANES = 8, SP_U = 3;
-template <int CB>
-__global__ void __launch_bounds__(SP_NT) csr_spmm_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+constexpr int SP_NT = 256, SP_LANES = 8;
+template <int CB, int SP_U, int MINB>
+__global__ void __launch_bounds__(SP_NT, MINB) csr_spmm_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx,
                                                          const cplx* __restrict__ vals, const cplx* __restrict__ V,
                                                          long long ldv, cplx* __restrict__ Y, long long ldy, long long n,
                                                          int c0, int ncand) {
@@ -138,10 +138,12 @@ cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* val
     const unsigned pgrid = (unsigned)((ncols + 255) / 256);
     for (int c0 = 0; c0 < C; c0 += 4) {
         const int nc = (C - c0 < 4) ? (C - c0) : 4;
-        if (nc == 1) csr_spmm_kernel<1><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, c0, nc);
+        // one candidate: latency bound on the dependent index -> gather chain, so occupancy beats unrolling (SP_U = 1, <= 32
+        // registers, 8 CTAs / SM; measured 0.132 vs 0.140 ms at n = 1M)
+        if (nc == 1) csr_spmm_kernel<1, 1, 8><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, c0, nc);
         else if (!pack_ws) {
-            if (nc == 2) csr_spmm_kernel<2><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, c0, nc);
-            else csr_spmm_kernel<4><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, c0, nc);
+            if (nc == 2) csr_spmm_kernel<2, 3, 1><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, c0, nc);
+            else csr_spmm_kernel<4, 3, 1><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, c0, nc);
         } else if (nc == 2) {
             spmm_pack_kernel<2><<<pgrid, 256, 0, stream>>>(V, ldv, pack_ws, ncols, c0, nc);
             csr_spmm_packed_kernel<2, 3><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, Y, ldy, n, c0, nc);
