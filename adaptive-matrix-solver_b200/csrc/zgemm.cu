@@ -5,17 +5,19 @@
 //
 // Design (B200): tcgen05 has no f64 kind, so the FP64 tensor pipe is reached with warp-level
 // mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; 37.1 TFLOP/s measured register-resident, profiles/fp64_peak_r01.txt).
-// A complex product is computed as ONE real product of twice the size: with A interleaved (re,im) along K and
-// B expanded on the fly to [[br, bi], [-bi, br]], the accumulator comes out interleaved (re,im) as well, so
-// global memory keeps numpy's complex128 layout end to end.
+// Two kernels share the TMA-bulk / mbarrier plumbing:
 //
-//   CTA tile 128 x 64 complex, 8 consumer warps (2 x 4), each 64 x 16 complex = 8 x 4 DMMA tiles (64 f64 accum),
-//   + 1 producer warp that stages the operands with cp.async.bulk (TMA bulk copies, SASS UBLKCP) into shared-memory
-//   rings guarded by full/empty mbarriers: A in 3 slabs of 16 complex k (2 KB copies), B in 2 slabs of 32 complex k
-//   (512 B copies -- measured: the bulk-copy path costs ~35 ns per copy per SM, so copy COUNT, not bytes, bounds the
-//   feed).  The kernel is persistent (one CTA per SM walks the tile list), the producer runs ahead across tiles and
-//   prefetches the next C tile into L2, from which the accumulators are initialised.  Column strides in shared
-//   memory are padded (132 / 34 complex) so that both fragment loads are bank-conflict free.
+//   zgemm_dmma_kernel    conventional complex product as ONE real product of twice the size: A interleaved (re,im) along K,
+//                        B expanded on the fly to [[br, bi], [-bi, br]], accumulator interleaved (re,im).  CTA tile 128 x 64,
+//                        8 consumer warps (64 x 16 each) + 1 producer warp.  Batched matvecs A*V, SVD products.
+//   zgemm3m_dmma_kernel  (further down) three real products per complex product (3M), 25 % fewer DMMA instructions;
+//                        CTA tile 128 x 48, asynchronous TMA epilogue.  All LU trailing updates.
+//
+// Common: the kernel is persistent (one CTA per SM walks the tile list, m-tile fastest so that concurrently running CTAs
+// share the B / U12 columns in L2); a producer warp stages the operands with cp.async.bulk (TMA bulk copies, SASS UBLKCP)
+// into shared-memory rings guarded by full/empty mbarriers and runs ahead across tile boundaries (measured: the bulk-copy
+// path costs ~35 ns per copy per SM, so copy COUNT, not bytes, bounds the feed -> few, large slabs); column strides in
+// shared memory are padded so that the fragment loads are bank-conflict free; numpy's complex128 layout end to end.
 #include <cstdlib>
 #include "zgemm.cuh"
 
