@@ -790,6 +790,28 @@ extern "C" int maus_step(maus_ctx* ctx, int64_t C, int problem_type, int method,
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Gram matrix of a set of (converged) candidate vectors -- the similarity tests of the reference's dedup / pruning
+// (AMS:436, 450, 515, 520: |np.vdot(v_i, v_j)| > 0.999) as ONE device pass instead of O(C^2) host vdots
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int maus_gram(maus_ctx* ctx, int64_t C, int64_t n, const double* V, double* G_out) {
+    if (!ctx || !V || !G_out || C <= 0 || n <= 0 || n > 0x7fffffffLL || C > 65535) return maus_fail(ctx, MAUS_E_ARG, "maus_gram: bad argument");
+    cudaSetDevice(ctx->device);
+    cplx *dV = nullptr, *dG = nullptr;
+    const size_t bv = (size_t)C * n * sizeof(cplx), bg = (size_t)C * C * sizeof(cplx);
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaMalloc(&dV, bv);
+    if (e == cudaSuccess) e = cudaMalloc(&dG, bg);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dV, V, bv, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = vec_gram(dV, (int)n, (int)C, dG, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(G_out, dG, bg, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dV); cudaFree(dG);
+    ctx->launches += 1;
+    if (e != cudaSuccess) return maus_fail(ctx, MAUS_E_CUDA, "maus_gram", e);
+    return MAUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // debug / parity hooks
 // ------------------------------------------------------------------------------------------------------------
 extern "C" int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, const double* A, const double* B, double* Cm,

@@ -442,6 +442,34 @@ __host__ inline int vmb_blocks(int n) {
     return want < 1 ? 1 : (want > VMB_MAXBLK ? VMB_MAXBLK : want);
 }
 
+// ---- Gram matrix of converged candidates (dedup tests |<v_i, v_j>| > 0.999, AMS:436, 450, 515, 520) ----------------------
+// G[i][j] = sum_k conj(v_i[k]) v_j[k] (= np.vdot(v_i, v_j)).  One CTA per (i, group of GR_J columns j): v_i is read once per
+// group, deterministic block reduction.  C is a few hundred at most and the vectors are L2 resident (C n 16 B).
+constexpr int GR_J = 4, GR_NT = 256;
+__global__ void __launch_bounds__(GR_NT) gram_kernel(const cplx* __restrict__ V, int n, int C, cplx* __restrict__ G) {
+    __shared__ double sh[GR_NT / 32];
+    const int i = blockIdx.x, j0 = blockIdx.y * GR_J;
+    const cplx* vi = V + (long long)i * n;
+    double ar[GR_J], ai[GR_J];
+#pragma unroll
+    for (int q = 0; q < GR_J; ++q) { ar[q] = 0.0; ai[q] = 0.0; }
+    for (int k = threadIdx.x; k < n; k += GR_NT) {
+        const cplx a = vi[k];
+#pragma unroll
+        for (int q = 0; q < GR_J; ++q) {
+            const int j = min(j0 + q, C - 1);
+            const cplx b = V[(long long)j * n + k];
+            ar[q] = fma(a.x, b.x, ar[q]); ar[q] = fma(a.y, b.y, ar[q]);      // conj(a) * b
+            ai[q] = fma(a.x, b.y, ai[q]); ai[q] = fma(-a.y, b.x, ai[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < GR_J; ++q) {
+        const double sr = block_sum(ar[q], sh), si = block_sum(ai[q], sh);
+        if (threadIdx.x == 0 && j0 + q < C) G[(long long)i * C + j0 + q] = cmake(sr, si);
+    }
+}
+
 }  // namespace
 
 cudaError_t vec_diag_amax(const cplx* A_rm, int n, cplx* diag, double* amax, cudaStream_t stream) {
@@ -452,6 +480,12 @@ cudaError_t vec_diag_amax(const cplx* A_rm, int n, cplx* diag, double* amax, cud
 cudaError_t vec_rowmajor_to_colmajor(const cplx* in_rm, cplx* out_cm, int n, cudaStream_t stream) {
     dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 32);
     transpose_kernel<<<grid, block, 0, stream>>>(in_rm, out_cm, n);
+    return cudaGetLastError();
+}
+
+cudaError_t vec_gram(const cplx* V, int n, int C, cplx* G, cudaStream_t stream) {
+    if (C <= 0) return cudaSuccess;
+    gram_kernel<<<dim3(C, (C + GR_J - 1) / GR_J), GR_NT, 0, stream>>>(V, n, C, G);
     return cudaGetLastError();
 }
 

@@ -34,3 +34,6 @@ cudaError_t vec_diag_amax(const cplx* A_rm, int n, cplx* diag, double* amax, cud
 // Y[c] (nrows) = A (nrows x ncols, row-major) * V[c] (ncols): rectangular variant for the SVD sweep
 cudaError_t vec_gemv_rect(const cplx* A_rm, int nrows, int ncols, const cplx* V, long long ldv, cplx* Y, long long ldy, int C,
                           cudaStream_t stream);
+
+// G[i][j] = <v_i, v_j> = sum_k conj(v_i[k]) v_j[k] for C vectors of length n ([C][n]); G is [C][C] row-major
+cudaError_t vec_gram(const cplx* V, int n, int C, cplx* G, cudaStream_t stream);

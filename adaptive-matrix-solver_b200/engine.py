@@ -248,6 +248,16 @@ class MausEngine:
                                                1 if negate else 0, int(use_dmma)))
         return Cm
 
+    def gram(self, V):
+        """G[i][j] = np.vdot(V[i], V[j]) for the rows of V ([C][n] complex128) in one device pass (dedup similarity tests)."""
+        V = _as_c128(V)
+        if V.ndim != 2:
+            raise ValueError("V must be [C][n]")
+        G = np.empty((V.shape[0], V.shape[0]), dtype=_c128)
+        if V.shape[0]:
+            self._check(self._lib.maus_gram(self._h, V.shape[0], V.shape[1], _dp(V), _dp(G)))
+        return G
+
     # -- SVD power-sweep branch (AMS:227-255, 300-301) -------------------------------------------------------
     def svd_set_matrix(self, A):
         A = _as_c128(A)

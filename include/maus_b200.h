@@ -153,6 +153,12 @@ int maus_svd_step(maus_ctx* ctx, int64_t C, double* U_io, double* V_io, double* 
 /* residual only (AMS:301) for host-replaced (u, v, sigma) */
 int maus_svd_residual(maus_ctx* ctx, int64_t C, const double* U, const double* V, const double* sigma, double* resid_out);
 
+/* ---- dedup / pruning similarity ------------------------------------------------------------------ */
+/* G[i][j] = <v_i, v_j> = np.vdot(v_i, v_j) for C host vectors V [C][n] (complex128); G_out [C][C] row-major complex128.
+ * Replaces the O(C^2) host vdots of the reference's converged-solution dedup and survivor pruning
+ * (Adaptive_Matrix_Solver_0.1.py:436, 450, 515, 520) by one device pass. */
+int maus_gram(maus_ctx* ctx, int64_t C, int64_t n, const double* V, double* G_out);
+
 /* ---- row-sharded sparse operator (BASELINE config 5 as worded) ---------------------------------- */
 /* Every rank owns n / world consecutive rows of A and the same slice of every vector; a matvec all-gathers its input,
  * GMRES all-reduces its dot products (NCCL over NVLink, bound at run time from `libpath` = the libnccl.so.2 the process

@@ -21,6 +21,10 @@ class FakeEngine:
             self.n = self.A[0].shape[0]
             self.A[1] = None
 
+    def gram(self, V):
+        V = np.asarray(V, dtype=np.complex128)
+        return V.conj() @ V.T
+
     def set_rhs(self, b):
         self.b = np.asarray(b, dtype=np.complex128)
 

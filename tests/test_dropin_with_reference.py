@@ -74,3 +74,42 @@ def test_seam_a_name_rebinding():
     s = ams.InverseIterateSolver(5, 1e-20, 25, 'iterative_gmres', True)
     assert (s.N, s.max_attempts, s.preferred_method, s.fallback_method, s.is_sparse) == (5, 25, 'iterative_gmres', 'direct_solve', True)
     pkg.GpuInverseIterateSolver.bind_engine(None)
+
+
+def test_device_vdot_leaves_the_reference_dedup_decisions_unchanged():
+    """the reference's own _update_global_diagnostics / _manage_candidates, run with np.vdot answered from
+    the Gram matrix, must take exactly the decisions they take with numpy's vdot."""
+    from adaptive_matrix_solver_b200.dedup import device_vdot
+    from fake_engine import FakeEngine
+    ams = load_reference(gmres_shim=True, name="ams_dropin_c")
+    n = 12
+
+    def population(seed):
+        s = _build(ams, n, 14, seed)
+        w, Vr = np.linalg.eig(np.asarray(s.M))
+        rng = np.random.default_rng(5)
+        for k, c in enumerate(s.candidates):
+            j = k % 5                                         # 5 distinct eigenpairs, several candidates on each
+            ph = np.exp(1j * rng.uniform(0, 6.28))
+            c.lambda_k = w[j]; c.v_k = (Vr[:, j] / np.linalg.norm(Vr[:, j])) * ph
+            c.residual_k = 1e-12 * (1 + k); c.w_k = 1.0
+            c.state = ams.SolutionCandidate.State.CONVERGED if k < 11 else ams.SolutionCandidate.State.EXPLORING
+        return s
+
+    ref, dev = population(3), population(3)
+    quiet(ref._update_global_diagnostics, 1)
+    np.random.seed(9); random.seed(9)
+    quiet(ref._manage_candidates, 1)
+    with device_vdot(ams, dev.candidates, FakeEngine()) as px:
+        quiet(dev._update_global_diagnostics, 1)
+    assert px.hits > 0
+    np.random.seed(9); random.seed(9)
+    with device_vdot(ams, dev.candidates, FakeEngine()) as px2:
+        quiet(dev._manage_candidates, 1)
+    assert px2.hits > 0
+    assert ams.np is np                                              # the proxy is gone
+    assert ref.num_distinct_converged_solutions == dev.num_distinct_converged_solutions == 5
+    assert [c.state for c in ref.candidates] == [c.state for c in dev.candidates]
+    assert len(ref.candidates) == len(dev.candidates)
+    assert np.allclose([c.lambda_k for c in ref.candidates if c.lambda_k is not None][:5],
+                       [c.lambda_k for c in dev.candidates if c.lambda_k is not None][:5])

@@ -125,3 +125,41 @@ def test_psi_perturbation_is_bounded_and_keyed(eng):
     assert np.abs(X1 - x0).max() < 0.15 * psi * n * x0 / (2.0 + psi)
     X3, _, _ = eng.solve_shifted([0j], [psi], rng_key=None, RHS=rhs[:1])
     assert np.abs(X3 - x0).max() < 1e-15            # no key -> no perturbation (sparse semantics, AMS:47)
+
+
+@pytest.mark.parametrize("C,n", [(1, 1), (2, 7), (5, 100), (37, 4096), (130, 513)])
+def test_gram_matches_numpy_vdot(eng, C, n):
+    """maus_gram: G[i][j] = np.vdot(v_i, v_j) (the dedup similarity tests AMS:436, 450, 515, 520 as one device pass)."""
+    rng = np.random.default_rng(C * 100 + n)
+    V = crand(rng, C, n)
+    V /= np.linalg.norm(V, axis=1, keepdims=True)
+    G = eng.gram(V)
+    ref = V.conj() @ V.T
+    assert np.abs(G - ref).max() <= 1e-14
+    assert np.abs(np.diag(G) - 1.0).max() <= 1e-14 and np.abs(G - G.conj().T).max() <= 1e-15
+
+
+def test_device_vdot_proxy_answers_from_the_gram_matrix(eng):
+    """dedup.device_vdot: vdot on converged candidates' vectors comes from the device, anything else falls through."""
+    import types
+    from adaptive_matrix_solver_b200.dedup import device_vdot
+    from mock_candidate import MockCandidate, ProblemType
+    rng = np.random.default_rng(4)
+    n = 300
+    A = crand(rng, n, n)
+    cands = [MockCandidate(A, ProblemType.EIGENVALUE, n) for _ in range(6)]
+    for k, c in enumerate(cands):
+        c.state = MockCandidate.State.CONVERGED if k != 3 else MockCandidate.State.EXPLORING
+    cands[4].v_k = cands[0].v_k * np.exp(0.7j)                      # a duplicate up to phase
+    mod = types.SimpleNamespace(np=np)
+    with device_vdot(mod, cands, eng) as px:
+        assert mod.np is px
+        for i in (0, 1, 2, 4, 5):
+            for j in (0, 1, 2, 4, 5):
+                assert abs(mod.np.vdot(cands[i].v_k, cands[j].v_k) - np.vdot(cands[i].v_k, cands[j].v_k)) <= 1e-14
+        assert px.hits == 25 and px.misses == 0
+        assert abs(abs(mod.np.vdot(cands[4].v_k, cands[0].v_k)) - 1.0) <= 1e-14
+        w = crand(rng, n)
+        assert mod.np.vdot(cands[3].v_k, w) == np.vdot(cands[3].v_k, w) and px.misses == 1     # not converged -> numpy
+        assert mod.np.abs(-2.0) == 2.0                                                          # everything else forwards
+    assert mod.np is np
