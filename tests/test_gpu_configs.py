@@ -1,0 +1,77 @@
+"""BASELINE.json configurations 4 and 5 at FULL size through the C ABI: size-independent properties (the oracle would need
+minutes per candidate here) plus one scipy cross-check where it is cheap.  K2 / K3 live in test_gpu_step_parity.py /
+test_gpu_edges.py."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import adaptive_matrix_solver_b200 as pkg
+    e = pkg.MausEngine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.timeout(600)
+def test_k4_dense_ill_conditioned_gmres_with_jacobi_full_size(eng):
+    """Config 4: dense Ax = b, n = 8192, cond ~ 1e9, GMRES(20) x 50 with the Jacobi preconditioner for stuck candidates
+    (AMS:61-90).  Every candidate must meet scipy's stopping rule, Jacobi must cut the iteration count, and the
+    preconditioned solve must replay scipy's iteration count and solution."""
+    from adaptive_matrix_solver_b200 import _abi
+    from adaptive_matrix_solver_b200.workloads import k4_system
+    n, C = 8192, 12
+    A, b = k4_system(n)
+    eng.set_matrix(A); eng.set_rhs(b)
+    rng = np.random.default_rng(0)
+    X0 = rng.standard_normal((C, n)) + 1j * rng.standard_normal((C, n))
+    eng.upload_vectors(X0)
+    jac = (np.arange(C) % 2).astype(np.uint8)
+    psi = np.full(C, 1e-19)
+    X, st, it = eng.solve_shifted(np.zeros(C, dtype=complex), psi, rng_key=np.arange(C, dtype=np.uint64), method=_abi.METHOD_GMRES,
+                                  use_jacobi=jac, RHS=None, rhs_shared=True)
+    assert (st == 0).all()
+    nb = np.linalg.norm(b)
+    for c in range(C):
+        assert np.linalg.norm(A @ X[c] - b) <= 1e-8 * nb * (1 + 1e-6)
+    assert it[jac == 1].max() < it[jac == 0].min()              # the preconditioner really acts
+    assert len(set(it[jac == 1].tolist())) == 1 and len(set(it[jac == 0].tolist())) == 1      # same system, same count
+    # scipy replay of one Jacobi candidate (x0 = b like AMS:89; a handful of dense matvecs)
+    d = np.diag(A) + psi[1]
+    M = spla.LinearOperator((n, n), matvec=lambda v: v / d, dtype=np.complex128)
+    cnt = []
+    H = spla.LinearOperator((n, n), matvec=lambda v: A @ v + psi[1] * v, dtype=np.complex128)      # H = A + psi I (AMS:47-52)
+    xr, info = spla.gmres(H, b, x0=b, rtol=1e-8, maxiter=50, M=M,
+                          callback=lambda r: cnt.append(r), callback_type="pr_norm")
+    assert info == 0 and len(cnt) == it[1]
+    assert np.linalg.norm(X[1] - xr) <= 1e-7 * np.linalg.norm(xr)
+
+
+@pytest.mark.timeout(900)
+def test_k5_sparse_million_row_gmres_full_size(eng):
+    """Config 5: sparse CSC, n = 1 000 000, ~21 nnz per row.  SpMM against scipy, GMRES meets rtol on every candidate with
+    one iteration count (same operator), and the long-vector kernels (RQ, residual) agree with numpy."""
+    from adaptive_matrix_solver_b200 import _abi
+    from adaptive_matrix_solver_b200.workloads import k5_sparse
+    n, C = 1_000_000, 5                                  # 5: one packed pass of 4 candidates + a single-candidate pass
+    A = k5_sparse(n)
+    rng = np.random.default_rng(1)
+    V = rng.random((C, n)) + 1j * rng.random((C, n)); V /= np.linalg.norm(V, axis=1, keepdims=True)
+    eng.set_matrix(A)
+    eng.upload_vectors(V)
+    lam, vn2 = eng.rq(C_=C)                                # SpMM (packed + unpacked kernels) + multi-block dots
+    AV = (A @ V.T).T
+    for c in range(C):
+        ref = np.vdot(V[c], AV[c])
+        assert abs(lam[c] - ref) <= 1e-12 * abs(ref) and abs(vn2[c] - 1) <= 1e-12
+    r = eng.residual(_abi.EIGENVALUE, lam=lam, C_=C)
+    for c in range(C):
+        ref = np.linalg.norm(AV[c] - lam[c] * V[c])
+        assert abs(r[c] - ref) <= 1e-11 * ref
+    X, st, it = eng.solve_shifted(np.zeros(C, dtype=complex), np.full(C, 5e-19), rng_key=None, method=_abi.METHOD_GMRES, RHS=None)
+    assert (st == 0).all() and len(set(it.tolist())) == 1 and 1 <= it[0] <= 40
+    for c in range(C):
+        assert np.linalg.norm(A @ X[c] - V[c]) <= 1e-8 * (1 + 1e-6)          # ||b|| = 1
