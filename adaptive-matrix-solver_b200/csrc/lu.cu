@@ -99,6 +99,7 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
     __shared__ cplx U12[IB][LU_NB];
     __shared__ int piv[LU_NB];
     __shared__ unsigned char is_piv[LU_NB];
+    __shared__ cplx pub[IB + 1];           // owner lane -> owner warp: the pivot row's window and 1/pivot
 
     int row[R];
     bool valid[R], done[R];
@@ -151,26 +152,28 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
                 const int owner_t = (cr % T) - rank * PANEL_NT;      // thread of this CTA that holds row cr
                 const int owner_q = cr / T;
                 if (warp == (owner_t >> 5)) {
+                    // the owner lane parks its window + 1/pivot in CTA-local shared memory (one hop instead of a chain of
+                    // 2 IB dependent shuffles), then the 32 lanes spread the remote (DSMEM) stores
                     const int ol = owner_t & 31;
-                    cplx keep = cmake(0.0, 0.0), rc = cmake(0.0, 0.0);
-                    const int e = lane % IB;
+                    if (lane == ol) {
 #pragma unroll
-                    for (int i = 0; i < IB; ++i) {
-                        cplx sel = a[0][i];
+                        for (int i = 0; i < IB; ++i) {
+                            cplx sel = a[0][i];
 #pragma unroll
-                        for (int q = 1; q < R; ++q) if (owner_q == q) sel = a[q][i];
-                        if (i == 0) {
-                            if (lane == ol) rc = crecip(sel);
-                            rc.x = __shfl_sync(0xffffffffu, rc.x, ol); rc.y = __shfl_sync(0xffffffffu, rc.y, ol);
+                            for (int q = 1; q < R; ++q) if (owner_q == q) sel = a[q][i];
+                            pub[i] = sel;
+                            if (i == 0) pub[IB] = crecip(sel);
                         }
-                        double vx = __shfl_sync(0xffffffffu, sel.x, ol), vy = __shfl_sync(0xffffffffu, sel.y, ol);
-                        if (i == e) keep = cmake(vx, vy);
                     }
+                    __syncwarp();
+                    const int e = lane % IB;
+                    const cplx keep = pub[e], rc = pub[IB];
                     for (int d = lane / IB; d < NC; d += 32 / IB) {
                         PanelSlot<IB>* s = cluster.map_shared_rank(&slots[j & 1][rank], d);
                         s->data[e] = keep;
                         if (e == 0) { s->val = cv; s->row = cr; s->recip = rc; }
                     }
+                    __syncwarp();          // pub is rewritten by the next column's owner only after the cluster barrier, but keep the warp together
                 }
             } else if (threadIdx.x == 0) {
                 for (int d = 0; d < NC; ++d) {
@@ -242,22 +245,30 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
                     for (int j = 0; j < IB; ++j) l[j] = (j < ibw) ? P[row[q] + (long long)(ib0 + j) * ld] : cmake(0.0, 0.0);
                     cplx* prow = P + row[q] + (long long)(ib0 + ibw) * ld;
                     const int rest4 = rest & ~3;
-                    cplx nx0, nx1, nx2, nx3;
-                    if (rest4 > 0) { nx0 = prow[0]; nx1 = prow[(long long)ld]; nx2 = prow[2LL * ld]; nx3 = prow[3LL * ld]; }
+                    // software pipeline two groups of four columns deep (three measured no better): the loads of columns c + 4 .. c + 11 are in flight
+                    // while columns c .. c + 3 are updated (the rows come from L2 / HBM, ~1 us away)
+                    cplx n0[4], n1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        n0[u] = (rest4 > 0) ? prow[(long long)u * ld] : cmake(0.0, 0.0);
+                        n1[u] = (rest4 > 4) ? prow[(long long)(4 + u) * ld] : cmake(0.0, 0.0);
+                    }
 #pragma unroll 1
                     for (int c = 0; c < rest4; c += 4) {
-                        cplx x0 = nx0, x1 = nx1, x2 = nx2, x3 = nx3;
-                        if (c + 4 < rest4) {
-                            nx0 = prow[(long long)(c + 4) * ld]; nx1 = prow[(long long)(c + 5) * ld];
-                            nx2 = prow[(long long)(c + 6) * ld]; nx3 = prow[(long long)(c + 7) * ld];
+                        cplx x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { x[u] = n0[u]; n0[u] = n1[u]; }
+                        if (c + 8 < rest4) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) n1[u] = prow[(long long)(c + 8 + u) * ld];
                         }
 #pragma unroll
                         for (int j = 0; j < IB; ++j) {
-                            cfms(x0, l[j], U12[j][c]); cfms(x1, l[j], U12[j][c + 1]);
-                            cfms(x2, l[j], U12[j][c + 2]); cfms(x3, l[j], U12[j][c + 3]);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) cfms(x[u], l[j], U12[j][c + u]);
                         }
-                        prow[(long long)c * ld] = x0; prow[(long long)(c + 1) * ld] = x1;
-                        prow[(long long)(c + 2) * ld] = x2; prow[(long long)(c + 3) * ld] = x3;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) prow[(long long)(c + u) * ld] = x[u];
                     }
                     for (int c = rest4; c < rest; ++c) {
                         cplx x = prow[(long long)c * ld];
