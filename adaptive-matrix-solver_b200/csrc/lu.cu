@@ -420,8 +420,17 @@ __global__ void __launch_bounds__(BS_NT) lu_backsolve_kernel(const cplx* __restr
         for (int i = tid; i < r0; i += BS_NT) {
             cplx acc = y[i];
             const cplx* u = Wb + i + (long long)r0 * n;
-#pragma unroll 8
-            for (int j = 0; j < bs; ++j) cfms(acc, __ldg(&u[(long long)j * n]), y[r0 + j]);
+            if (bs == BS_BLK) {
+                // all 32 loads of the row segment in flight before the first FMA (the kernel is bound by HBM latency x
+                // bytes in flight per SM: one CTA per SM streams the whole upper triangle)
+                cplx uu[BS_BLK];
+#pragma unroll
+                for (int j = 0; j < BS_BLK; ++j) uu[j] = __ldcs(&u[(long long)j * n]);
+#pragma unroll
+                for (int j = 0; j < BS_BLK; ++j) cfms(acc, uu[j], y[r0 + j]);
+            } else {
+                for (int j = 0; j < bs; ++j) cfms(acc, __ldg(&u[(long long)j * n]), y[r0 + j]);
+            }
             y[i] = acc;
         }
         __syncthreads();
