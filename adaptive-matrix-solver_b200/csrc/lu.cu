@@ -341,6 +341,12 @@ __global__ void __launch_bounds__(256) lu_permute_rows_kernel(cplx* W, long long
 // thread c owns column c of X = L11^-1; X is kept packed (row p holds columns 0..p) in shared memory.  Rows of L11 are
 // streamed through a ring of TRTRI_PF row buffers with cp.async so the global-load latency of row r + TRTRI_PF - 1
 // hides behind the arithmetic of rows r .. r + TRTRI_PF - 2 (the one-row-ahead version was latency-bound: 353 us).
+//
+// The row recurrence is sequential (two CTA barriers per row), so the block is split in two halves of h = jb / 2 rows:
+//   phase A  inverts the two diagonal blocks X11, X22 SIMULTANEOUSLY (threads c < h work on row rl, threads c >= h on row
+//            h + rl of the same iteration): h - 1 instead of jb - 1 sequential steps;
+//   phase B  X21 = -X22 (L21 X11): two h x h x h triangular products spread over all threads (T = L21 X11 goes into X21's
+//            slots, then X21 row by row from the bottom up, in place).
 constexpr int TRTRI_PF = 8;
 constexpr int TRTRI_SPLIT = 4;     // lanes sharing one column's dot product (critical path / 4)
 __global__ void __launch_bounds__(LU_NB * TRTRI_SPLIT) lu_trtri_kernel(const cplx* __restrict__ W, long long strideW, int n, int k0,
@@ -350,31 +356,70 @@ __global__ void __launch_bounds__(LU_NB * TRTRI_SPLIT) lu_trtri_kernel(const cpl
     cplx* rowbuf = X + (LU_NB * (LU_NB + 1)) / 2;                  // TRTRI_PF x LU_NB ring of rows of L
     const int b = blockIdx.x, c = threadIdx.x / TRTRI_SPLIT, sp = threadIdx.x % TRTRI_SPLIT;
     const cplx* L = W + (long long)b * strideW + (long long)k0 * n + k0;   // L[r + p*n]
+    const int h = (jb >= 32 && (jb & 1) == 0) ? jb / 2 : jb;       // half size (h == jb: one block, no phase B)
+    const int base = (c >= h) ? h : 0;                             // first row / column of this thread's diagonal block
     if (c < jb && sp == 0) X[(c * (c + 1)) / 2 + c] = cmake(1.0, 0.0);
-    auto fetch_row = [&](int r) {
-        if (r < jb && c < r && sp == 0) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&rowbuf[(r % TRTRI_PF) * LU_NB + c]);
+    // ring slot entry c holds L[base + rl][c]: the top block's row rl for c < h, the bottom block's row h + rl for c >= h
+    auto fetch_row = [&](int rl) {
+        const int r = base + rl;
+        if (rl < h && r < jb && c < r && sp == 0) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&rowbuf[(rl % TRTRI_PF) * LU_NB + c]);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(L + r + (long long)c * n) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    for (int r = 1; r < TRTRI_PF; ++r) fetch_row(r);
-    for (int r = 1; r < jb; ++r) {
-        fetch_row(r + TRTRI_PF - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(TRTRI_PF - 1) : "memory");     // row r has landed (for this thread)
+    for (int rl = 1; rl < TRTRI_PF; ++rl) fetch_row(rl);
+    for (int rl = 1; rl < h; ++rl) {
+        fetch_row(rl + TRTRI_PF - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(TRTRI_PF - 1) : "memory");     // row rl has landed (for this thread)
         __syncthreads();                                                             // ... and for every thread
-        const cplx* lr = rowbuf + (r % TRTRI_PF) * LU_NB;
+        const cplx* lr = rowbuf + (rl % TRTRI_PF) * LU_NB;
+        const int r = base + rl;
         {
             cplx acc = cmake(0.0, 0.0);
-            if (c < r)
+            if (c < r && r < jb)
                 for (int p = c + sp; p < r; p += TRTRI_SPLIT) cfms(acc, lr[p], X[(p * (p + 1)) / 2 + c]);
 #pragma unroll
             for (int o = TRTRI_SPLIT / 2; o > 0; o >>= 1) {
                 acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
             }
-            if (c < r && sp == 0) X[(r * (r + 1)) / 2 + c] = acc;
+            if (c < r && r < jb && sp == 0) X[(r * (r + 1)) / 2 + c] = acc;
         }
-        __syncthreads();       // X row r complete; ring slot r % PF may be refilled by the next fetch
+        __syncthreads();       // X row complete; ring slot rl % PF may be refilled by the next fetch
+    }
+    if (h < jb) {
+        // ---- phase B: X21 = -X22 * (L21 * X11) ----
+        // T[i][j] = sum_{p = j}^{h-1} L21[i][p] X11[p][j]  -> slot of X21[i][j]; thread t: i = t % h, columns j = t / h + u * (NT / h)
+        const int NT = LU_NB * TRTRI_SPLIT;
+        {
+            const int i = threadIdx.x % h;
+            const cplx* l21 = L + (h + i);                         // L21[i][p] = l21[p * n] (consecutive threads, consecutive rows)
+            for (int j = threadIdx.x / h; j < h; j += NT / h) {
+                cplx acc = cmake(0.0, 0.0);
+                for (int p = j; p < h; ++p) cfma(acc, __ldg(&l21[(long long)p * n]), X[(p * (p + 1)) / 2 + j]);
+                X[((h + i) * (h + i + 1)) / 2 + j] = acc;
+            }
+        }
+        __syncthreads();
+        // X21[i][j] = -sum_{q <= i} X22[i][q] T[q][j], rows from the bottom up so that T[q <= i][j] is still intact; column j
+        // is owned by a group of 8 lanes (dot product split over them)
+        {
+            const int j = threadIdx.x >> 3, l8 = threadIdx.x & 7;
+            for (int i = h - 1; i >= 0; --i) {
+                cplx acc = cmake(0.0, 0.0);
+                if (j < h) {
+                    const cplx* x22 = X + ((h + i) * (h + i + 1)) / 2 + h;       // X22[i][q], q <= i
+                    for (int q = l8; q <= i; q += 8) cfma(acc, x22[q], X[((h + q) * (h + q + 1)) / 2 + j]);
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                }
+                if (j < h && l8 == 0) X[((h + i) * (h + i + 1)) / 2 + j] = cmake(-acc.x, -acc.y);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
     }
     cplx* out = Linv + (long long)b * LU_NB * LU_NB;
     for (int r = sp; r < jb; r += TRTRI_SPLIT)
