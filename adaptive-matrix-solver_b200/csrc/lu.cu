@@ -542,9 +542,13 @@ cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batc
     if (force_r == 1) mode = 0; else if (force_r == 2) mode = 2; else if (force_r == 3) mode = 1;
     if (m > PANEL_MAXC * 512) mode = 2;
     const int rows_per_cta = (mode == 0) ? 512 : (mode == 1 ? 512 : 1024);
+    // cluster size = exactly the CTAs the panel's rows need (1..8, not rounded up to a power of two: a CTA without rows
+    // would still occupy its half SM for the whole column loop)
+    static int pow2 = -1;
+    if (pow2 < 0) { const char* e = getenv("MAUS_PANEL_POW2"); pow2 = (e && atoi(e)) ? 1 : 0; }
     int need = (m + rows_per_cta - 1) / rows_per_cta;
-    int nc = 1;
-    while (nc < need) nc <<= 1;
+    int nc = need < 1 ? 1 : need;
+    if (pow2) { nc = 1; while (nc < need) nc <<= 1; }
     if (mode == 0) return launch_panel<1, 16, 512>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
     if (mode == 1) return launch_panel<2, 8, 256>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
     return launch_panel<2, 8, 512>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
