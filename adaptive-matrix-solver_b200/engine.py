@@ -248,6 +248,16 @@ class MausEngine:
                                                1 if negate else 0, int(use_dmma)))
         return Cm
 
+    def project(self, Ec, V):
+        """P[c] = E^H v_c for the rows of V ([C][n]) -- the similarity scores of the Hermitian shortcut (AMS:165) as one
+        tensor-pipe GEMM.  ``Ec`` = conj(E) in C order ([n][m], i.e. E^H stored column-major); returns [C][m]."""
+        Ec = _as_c128(Ec); V = _as_c128(V)
+        n, m = Ec.shape
+        if V.ndim != 2 or V.shape[1] != n:
+            raise ValueError("V must be [C][n]")
+        out = np.zeros((1, V.shape[0], m), dtype=_c128)
+        return self.debug_zgemm(Ec[None], V[None], out, beta=0, negate=False, use_dmma=1)[0]
+
     def gram(self, V):
         """G[i][j] = np.vdot(V[i], V[j]) for the rows of V ([C][n] complex128) in one device pass (dedup similarity tests)."""
         V = _as_c128(V)

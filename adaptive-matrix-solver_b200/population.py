@@ -100,20 +100,25 @@ def step_population(candidates, M, b, strat_params, problem_knowledge, engine, c
     State = type(candidates[0]).State
     live = [c for c in candidates if c.state not in (State.CONVERGED, State.RETIRED)]          # AMS:575
     hermitian = bool(problem_knowledge.get('is_hermitian', False))
-    gpu, svd = [], []
+    gpu, svd, herm = [], [], []
     for c in live:
         pt = c.problem_type.value
         if pt == _abi.SOLVE_LINEAR_SYSTEM or (pt == _abi.EIGENVALUE and not hermitian):
             gpu.append(c)
         elif pt == _abi.SVD and hasattr(engine, "svd_step") and c.problem_matrix is M and not _is_sparse(M):
             svd.append(c)                     # SVD power sweep (AMS:227-255): the first "next" row, SURVEY.md 8f-1
+        elif (pt == _abi.EIGENVALUE and hermitian and not _is_sparse(M) and hasattr(engine, "project")
+              and isinstance(c.v_k, np.ndarray)):
+            herm.append(c)                    # dense Hermitian shortcut with ONE shared eigh
         else:
-            # Hermitian shortcut (AMS:155-221) is not on the hot path: untouched
+            # sparse Hermitian shortcut (eigsh, AMS:187-213) and anything else: the reference method, untouched
             c.update_solution_step(M, b, strat_params, problem_knowledge)
     if svd:
         _step_group_svd(svd, M, b, strat_params, engine, State)
+    if herm:
+        _step_group_hermitian(herm, M, b, strat_params, problem_knowledge, engine, State)
     if not gpu:
-        return len(svd)
+        return len(svd) + len(herm)
     cache = cache if cache is not None else getattr(engine, "_matrix_cache", None)
     if cache is None:
         cache = engine._matrix_cache = _MatrixCache()
@@ -346,6 +351,58 @@ def install_dropin(ams_module, engine):
     GpuInverseIterateSolver.bind_engine(engine)
     ams_module.InverseIterateSolver = GpuInverseIterateSolver
     return ams_module
+
+
+def _step_group_hermitian(cands, M, b, strat_params, problem_knowledge, engine, State):
+    """Dense Hermitian shortcut (AMS:155-186) for a whole group.  The reference calls ``sla.eigh(current_matrix_A)`` inside
+    EVERY candidate's step -- C identical O(n^3) factorizations per generation.  Here the same LAPACK call runs ONCE (same
+    eigenpairs, bit for bit), the similarity scores |v_k^H E| of all candidates are one device GEMM (``engine.project``) and
+    the residuals one batched device pass.  A failing eigh falls back to the reference method per candidate (AMS:182-185)."""
+    import scipy.linalg as sla
+    cache = getattr(engine, "_eigh_cache", None)
+    try:
+        if cache is None or cache[0] is not M:
+            w, E = sla.eigh(M)                                                      # AMS:161
+            cache = engine._eigh_cache = (M, w, E, np.ascontiguousarray(E.conj()))  # conj(E) C-order = E^H column-major
+    except Exception:                                                              # AMS:182-185: "Falling back."
+        for c in cands:
+            c.update_solution_step(M, b, strat_params, problem_knowledge)
+        return
+    _, w, E, Ec = cache
+    n = E.shape[0]
+    usable = [c for c in cands if c.v_k.shape[0] == n and E.shape[1] > 0]
+    for c in cands:
+        if c not in usable:
+            c.update_solution_step(M, b, strat_params, problem_knowledge)
+    if not usable:
+        return
+    V = np.ascontiguousarray(np.stack([c.v_k for c in usable]), dtype=np.complex128)
+    scores = np.abs(engine.project(Ec, V))                                          # |E^H v| = |v^H E| (AMS:165), [C][n]
+    best = np.argmax(scores, axis=1)                                                # AMS:169
+    Vn = np.empty_like(V)
+    lam = np.empty(len(usable), dtype=np.complex128)
+    for k, c in enumerate(usable):
+        c.b_vector = b                                                              # AMS:146
+        c.prev_residual = c.residual_k                                              # AMS:147
+        v = E[:, best[k]].astype(np.complex128, copy=True)
+        v /= np.linalg.norm(v)                                                      # AMS:173
+        Vn[k] = v
+        lam[k] = w[best[k]]
+    cache_m = getattr(engine, "_matrix_cache", None)
+    if cache_m is None:
+        cache_m = engine._matrix_cache = _MatrixCache()
+    cache_m.ensure(engine, M, 0, 'dense')
+    resid = engine.residual(_abi.EIGENVALUE, Vn, lam)                               # AMS:175, batched
+    for k, c in enumerate(usable):
+        c.lambda_k = w[best[k]]                                                     # a real float64, like the reference (AMS:171)
+        c.v_k = Vn[k].copy()
+        c.residual_k = np.float64(resid[k])
+        c.state = State.CONVERGED                                                   # AMS:176-179
+        c.stuck_counter = 0
+        c.local_psi_retries_needed = 0
+        c.w_k = 1.0
+        c.param_history.append(c.get_current_solution_params())                     # AMS:216-217
+        c.residual_history.append(c.residual_k)
 
 
 def gpu_generation(maus_solver, iteration, engine):

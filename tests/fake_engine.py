@@ -21,6 +21,13 @@ class FakeEngine:
             self.n = self.A[0].shape[0]
             self.A[1] = None
 
+    def project(self, Ec, V):
+        return (np.asarray(Ec).T @ np.asarray(V, dtype=np.complex128).T).T
+
+    def residual(self, problem_type, V=None, lam=None, C_=None, res_slot=0):
+        A = self.A[0]
+        return np.array([np.linalg.norm(A @ V[c] - lam[c] * V[c]) for c in range(V.shape[0])])
+
     def gram(self, V):
         V = np.asarray(V, dtype=np.complex128)
         return V.conj() @ V.T

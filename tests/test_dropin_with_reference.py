@@ -113,3 +113,42 @@ def test_device_vdot_leaves_the_reference_dedup_decisions_unchanged():
     assert len(ref.candidates) == len(dev.candidates)
     assert np.allclose([c.lambda_k for c in ref.candidates if c.lambda_k is not None][:5],
                        [c.lambda_k for c in dev.candidates if c.lambda_k is not None][:5])
+
+
+def test_hermitian_shortcut_with_one_shared_eigh_equals_the_reference_loop():
+    """the dense Hermitian shortcut (AMS:155-186) runs eigh ONCE for the group and matches every candidate on
+    the device; the outcome per candidate must equal the reference's own per-candidate eigh."""
+    from adaptive_matrix_solver_b200.population import step_population
+    from fake_engine import FakeEngine
+    ams = load_reference(gmres_shim=True, name="ams_dropin_h")
+
+    def build(seed):
+        np.random.seed(seed); random.seed(seed)
+        M = ams.create_laplace_like_complex_eigen_for_MAUS(18, make_hermitian=True)
+        return quiet(ams.MAUS_Solver, M, problem_type=ams.ProblemType.EIGENVALUE, initial_num_candidates=9, global_convergence_tol=1e-9)
+
+    ref, dev = build(11), build(11)
+    assert ref.problem_knowledge.get('is_hermitian', False)
+    for c in ref.candidates:
+        quiet(c.update_solution_step, ref.M, ref.b, ref.strat_params, ref.problem_knowledge)
+    eng = FakeEngine()
+    calls = {"n": 0}
+    import scipy.linalg as sla
+    real_eigh = sla.eigh
+
+    def counting_eigh(*a, **k):
+        calls["n"] += 1
+        return real_eigh(*a, **k)
+    sla.eigh = counting_eigh
+    try:
+        n_stepped = quiet(step_population, dev.candidates, dev.M, dev.b, dev.strat_params, dev.problem_knowledge, eng)
+    finally:
+        sla.eigh = real_eigh
+    assert n_stepped == 9 and calls["n"] == 1                        # one factorization for the whole population
+    for a, b_ in zip(ref.candidates, dev.candidates):
+        assert a.state == b_.state == ams.SolutionCandidate.State.CONVERGED
+        assert a.lambda_k == b_.lambda_k and type(a.lambda_k) is type(b_.lambda_k)
+        assert np.array_equal(a.v_k, b_.v_k)
+        assert abs(a.residual_k - b_.residual_k) <= 1e-13
+        assert a.w_k == b_.w_k == 1.0 and a.stuck_counter == b_.stuck_counter == 0
+        assert len(a.residual_history) == len(b_.residual_history) and len(a.param_history) == len(b_.param_history)

@@ -260,3 +260,30 @@ def test_long_vectors_use_multi_block_reductions(eng):
     Z = np.zeros((1, n), dtype=np.complex128)
     lam0, vn20 = eng.rq(Z)
     assert lam0[0] == 0 and vn20[0] == 0
+
+
+def test_dense_hermitian_group_shares_one_eigh_and_matches_on_the_device(eng):
+    """SURVEY.md 8f-3 (AMS:155-186): one host eigh for the group, |v^H E| as a device GEMM, batched residuals."""
+    from adaptive_matrix_solver_b200 import step_population
+    rng = np.random.default_rng(21)
+    n, C = 300, 7
+    B = crand(rng, n, n)
+    A = (B + B.conj().T) / 2
+    import scipy.linalg as sla
+    w, E = sla.eigh(A)                                            # the reference's call (AMS:161)
+    P = eng.project(np.ascontiguousarray(E.conj()), crand(rng, 3, n))
+    assert P.shape == (3, n)
+    cands = [MockCandidate(A, ProblemType.EIGENVALUE, n) for _ in range(C)]
+    targets = rng.choice(n, C, replace=False)
+    for c, t in zip(cands, targets):
+        v = E[:, t] + 0.2 * crand(rng, n) / np.sqrt(n)            # nearest eigenvector is column t
+        c.v_k = v / np.linalg.norm(v)
+    strat = dict(overall_psi_aggression_factor=1.0, max_psi_retries=25, current_convergence_threshold=1e-10)
+    know = dict(local_solver_preference="direct_solve", is_sparse_problem=False, is_hermitian=True)
+    hist = [len(c.residual_history) for c in cands]
+    assert step_population(cands, A, None, strat, know, eng) == C
+    for c, t, h in zip(cands, targets, hist):
+        assert c.state == MockCandidate.State.CONVERGED and c.w_k == 1.0 and c.stuck_counter == 0
+        assert c.lambda_k == w[t]
+        assert np.array_equal(c.v_k, E[:, t] / np.linalg.norm(E[:, t]))
+        assert c.residual_k <= 1e-12 * np.abs(w).max() * 10 and len(c.residual_history) == h + 1
