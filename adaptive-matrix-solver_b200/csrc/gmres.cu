@@ -59,6 +59,8 @@ struct GmresWs {
     int* counters = nullptr;      // [0] = inner_active count, [1] = active count
     int* jacbad = nullptr;        // [C]
     cplx* red = nullptr;          // [C] compact reduction record (row-sharded mode)
+    int* active_idx = nullptr;    // [C] indices of the candidates still iterating (matvec compaction)
+    cplx *vc = nullptr, *zc = nullptr;   // [C][n] compacted matvec input / output (allocated when first needed)
     size_t bytes = 0;
 };
 
@@ -94,6 +96,32 @@ __global__ void gm_expand_kernel(cplx* __restrict__ partial, const cplx* __restr
     if (b >= C) return;
     partial[b * GM_MAXBLK] = red[b];
     for (int q = 1; q < nblk; ++q) partial[b * GM_MAXBLK + q] = cmake(0.0, 0.0);
+}
+
+// ---- matvec compaction ---------------------------------------------------------------------------------------------------
+// Candidates leave the iteration at different times (a Jacobi-preconditioned one after a handful of steps, a plain one after
+// hundreds: BASELINE config 4).  The matvec is the only kernel that cannot skip a finished candidate by itself (a GEMM / SpMM
+// over all C columns), so once a quarter of the batch is done the still-active columns are gathered into a compact block.
+__global__ void gm_list_active_kernel(const GmresCand* __restrict__ cand, int C, int* __restrict__ idx) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int a = 0;
+    for (int b = 0; b < C; ++b) if (cand[b].active) idx[a++] = b;      // increasing order: deterministic
+}
+__global__ void gm_gather_kernel(const cplx* __restrict__ src, long long ld, const int* __restrict__ idx, cplx* __restrict__ dst,
+                                 long long n, int nblk) {
+    const int a = blockIdx.y;
+    long long i0, i1; chunk_range(n, nblk, blockIdx.x, i0, i1);
+    const cplx* s = src + (long long)idx[a] * ld;
+    cplx* d = dst + (long long)a * n;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) d[i] = s[i];
+}
+__global__ void gm_scatter_kernel(const cplx* __restrict__ src, const int* __restrict__ idx, cplx* __restrict__ dst, long long ld,
+                                  long long n, int nblk) {
+    const int a = blockIdx.y;
+    long long i0, i1; chunk_range(n, nblk, blockIdx.x, i0, i1);
+    const cplx* s = src + (long long)a * n;
+    cplx* d = dst + (long long)idx[a] * ld;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) d[i] = s[i];
 }
 
 // ---- setup ------------------------------------------------------------------------------------------------------
@@ -472,7 +500,7 @@ void maus_gmres_free(maus_ctx* ctx) {
     GmresWs* ws = (GmresWs*)ctx->gmres;
     if (!ws) return;
     cudaFree(ws->Vk); cudaFree(ws->w); cudaFree(ws->z); cudaFree(ws->x); cudaFree(ws->r); cudaFree(ws->minv);
-    cudaFree(ws->partial); cudaFree(ws->cand); cudaFree(ws->counters); cudaFree(ws->jacbad); cudaFree(ws->red);
+    cudaFree(ws->partial); cudaFree(ws->cand); cudaFree(ws->counters); cudaFree(ws->jacbad); cudaFree(ws->red); cudaFree(ws->active_idx); cudaFree(ws->vc); cudaFree(ws->zc);
     ctx->bytes_held -= (long long)ws->bytes;
     delete ws;
     ctx->gmres = nullptr;
@@ -497,6 +525,7 @@ static int gmres_ensure(maus_ctx* ctx, long long n, long long C, GmresWs** out) 
     GM_ALLOC(ws->counters, 2 * sizeof(int));
     GM_ALLOC(ws->jacbad, (size_t)ws->C * sizeof(int));
     GM_ALLOC(ws->red, (size_t)ws->C * sizeof(cplx));
+    GM_ALLOC(ws->active_idx, (size_t)ws->C * sizeof(int));
 #undef GM_ALLOC
     ws->bytes = total;
     ctx->bytes_held += (long long)total;
@@ -542,9 +571,20 @@ int gmres_core(maus_ctx* ctx, const GmresOperator& op, long long C, const cplx* 
     gm_after_norms_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk);
     ctx->launches += 4;
 
+    long long n_compact = 0;          // > 0: ws->active_idx lists that many still-active candidates, matvecs run on them only
     auto matvec = [&](const cplx* v, long long ldv) -> int {
-        int r2 = op.matvec(v, ldv, ws->z, n, C);
-        if (r2) return r2;
+        int r2;
+        if (n_compact > 0) {
+            const dim3 gridg(nblk, (unsigned)n_compact);
+            gm_gather_kernel<<<gridg, GM_NT, 0, st>>>(v, ldv, ws->active_idx, ws->vc, n, nblk);
+            r2 = op.matvec(ws->vc, n, ws->zc, n, n_compact);
+            if (r2) return r2;
+            gm_scatter_kernel<<<gridg, GM_NT, 0, st>>>(ws->zc, ws->active_idx, ws->z, n, n, nblk);
+            ctx->launches += 2;
+        } else {
+            r2 = op.matvec(v, ldv, ws->z, n, C);
+            if (r2) return r2;
+        }
         if (any_perturb) {
             // launched only if some candidate's psi puts R above rounding; per-candidate test inside the kernel
             const int wpb = 8;
@@ -605,6 +645,20 @@ int gmres_core(maus_ctx* ctx, const GmresOperator& op, long long C, const cplx* 
         MAUS_CUDA(ctx, cudaMemcpyAsync(host_counters, ws->counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         MAUS_CUDA(ctx, cudaStreamSynchronize(st));
         n_active = host_counters[1];
+        // compaction pays once a quarter of the batch has finished (and changes the passes of 4 of the SpMM / the GEMM width)
+        if (n_active > 0 && n_active * 4 <= C * 3 && n_active != n_compact) {
+            if (!ws->vc) {
+                const size_t vec = (size_t)ws->C * n * sizeof(cplx);
+                if (cudaMalloc((void**)&ws->vc, vec) != cudaSuccess || cudaMalloc((void**)&ws->zc, vec) != cudaSuccess) {
+                    cudaFree(ws->vc); ws->vc = nullptr; cudaGetLastError();          // no memory: keep the full-width matvec
+                } else { ws->bytes += 2 * vec; ctx->bytes_held += (long long)(2 * vec); }
+            }
+            if (ws->vc) {
+                gm_list_active_kernel<<<1, 1, 0, st>>>(ws->cand, (int)C, ws->active_idx);
+                ctx->launches += 1;
+                n_compact = n_active;
+            }
+        }
     }
     gm_finish_kernel<<<gridv, GM_NT, 0, st>>>(ws->cand, ws->x, n, X, status, iters, nblk);
     ctx->launches += 1;

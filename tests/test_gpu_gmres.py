@@ -151,3 +151,29 @@ def test_step_population_replays_reference_gmres_golden(eng, name, stride):
         assert abs(c.residual_k - after["res"]) <= 1e-6 * abs(after["res"]) + gfloor, (name, i, c.residual_k, after["res"])
         checked += 1
     assert checked > 20
+
+
+def test_matvec_compaction_keeps_every_candidate_on_scipys_iteration(eng):
+    """Candidates that finish early (Jacobi) are dropped from the batched matvec (gmres.cu: matvec compaction); the ones still
+    iterating must not notice: same iteration counts as scipy, same solutions as when they are solved without fast peers."""
+    from adaptive_matrix_solver_b200 import _abi
+    n, C = 320, 16
+    rng = np.random.default_rng(31)
+    d = np.logspace(0, 3.5, n) * np.exp(1j * rng.uniform(0, 0.3, n))
+    A = np.diag(d) + 0.05 * crand(rng, n, n)
+    RHS = crand(rng, C, n)
+    jac = (np.arange(C) % 4 != 0).astype(np.uint8)               # 12 fast (Jacobi) candidates, 4 slow ones
+    eng.set_matrix(A)
+    zero, psi = np.zeros(C, dtype=complex), np.full(C, 1e-19)
+    X, st, it = eng.solve_shifted(zero, psi, rng_key=None, method=_abi.METHOD_GMRES, use_jacobi=jac, RHS=RHS)
+    slow = np.flatnonzero(jac == 0)
+    assert it[jac == 1].max() < 20 < it[slow].min()               # the slow ones run several restart cycles alone
+    Xs, sts, its = eng.solve_shifted(zero[slow], psi[slow], rng_key=None, method=_abi.METHOD_GMRES, use_jacobi=jac[slow], RHS=RHS[slow])
+    assert np.array_equal(it[slow], its) and np.array_equal(st[slow], sts)
+    for k, c in enumerate(slow):
+        assert np.linalg.norm(X[c] - Xs[k]) <= 1e-11 * np.linalg.norm(Xs[k])
+    H = A + 1e-19 * np.eye(n)
+    for c in (0, 1):
+        M = np.diag(1.0 / np.diag(H)) if jac[c] else None
+        xr, info, nit = scipy_gmres(H, RHS[c], M)
+        assert (st[c] == 0) == (info == 0) and it[c] == nit
