@@ -75,3 +75,27 @@ def test_k5_sparse_million_row_gmres_full_size(eng):
     assert (st == 0).all() and len(set(it.tolist())) == 1 and 1 <= it[0] <= 40
     for c in range(C):
         assert np.linalg.norm(A @ X[c] - V[c]) <= 1e-8 * (1 + 1e-6)          # ||b|| = 1
+
+
+@pytest.mark.timeout(600)
+def test_direct_solve_at_the_maximum_order(eng):
+    """n = 8192 is the largest order of the batched LU (one panel cluster owns all rows, two rows per thread): backward error
+    of the shifted solves and agreement of the Rayleigh quotients with numpy."""
+    from adaptive_matrix_solver_b200 import _abi
+    from adaptive_matrix_solver_b200.workloads import k2_matrix, initial_vectors
+    n, C = 8192, 2
+    A = k2_matrix(n, seed=3)
+    V = initial_vectors(C, n, seed=5)
+    eng.set_matrix(A)
+    eng.upload_vectors(V)
+    lam, _ = eng.rq(C_=C)
+    for c in range(C):
+        assert abs(lam[c] - np.vdot(V[c], A @ V[c])) <= 1e-12 * abs(lam[c])
+    psi = np.full(C, 1e-20)
+    X, st, _ = eng.solve_shifted(lam, psi, rng_key=np.arange(C, dtype=np.uint64) + 1, method=_abi.METHOD_LU, RHS=V)
+    assert (st == 0).all()
+    anorm = np.abs(A).sum(axis=1).max()
+    for c in range(C):
+        r = A @ X[c] - (lam[c] - psi[c]) * X[c] - V[c]
+        be = np.linalg.norm(r) / (anorm * np.linalg.norm(X[c]) + np.linalg.norm(V[c]))
+        assert be < 1e-13, be
