@@ -51,6 +51,8 @@ void prof_tag(maus_ctx* ctx, int h, int M, int N, int K, int batch) {
     if (h >= 0) ctx->prof.tag[h / 2] = ((long long)M << 40) | ((long long)N << 24) | ((long long)K << 8) | (long long)(batch & 0xff);
 }
 
+static int lu_use_3m();
+
 int prof_begin(maus_ctx* ctx, int kind, double work) {
     ProfAccum& pr = ctx->prof;
     if (!pr.enabled) return -1;
@@ -409,6 +411,14 @@ int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cpl
             p.B = V; p.ldb = ldv; p.strideB = 0;
             p.C = Y; p.ldc = ldy; p.strideC = 0;
             p.M = (int)n; p.N = (int)C; p.K = (int)n; p.batch = 1; p.beta = 0; p.negate = 0;
+            // skinny product (few row tiles): pick the kernel with the smaller (rounds over the SMs) x (work per tile):
+            // 4-product kernel 128 x 64 tiles at 8 flops, 3M kernel 128 x 48 tiles at 6 flops per complex multiply-add
+            {
+                const long long sms = ctx->sm_count > 0 ? ctx->sm_count : MAUS_SM_COUNT_B200;
+                const long long mt = (n + 127) / 128, t4 = mt * ((C + 63) / 64), t3 = mt * ((C + 47) / 48);
+                const long long est4 = ((t4 + sms - 1) / sms) * 64 * 8, est3 = ((t3 + sms - 1) / sms) * 48 * 6;
+                p.algo3m = (lu_use_3m() && est3 < est4) ? 1 : 0;
+            }
             int h = prof_begin(ctx, MAUS_PROF_MATVEC_GEMM, 8.0 * n * (double)n * C);
             MAUS_CUDA(ctx, zgemm_dmma_launch(p, ctx->stream));
             prof_end(ctx, h);
