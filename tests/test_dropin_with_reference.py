@@ -152,3 +152,27 @@ def test_hermitian_shortcut_with_one_shared_eigh_equals_the_reference_loop():
         assert abs(a.residual_k - b_.residual_k) <= 1e-13
         assert a.w_k == b_.w_k == 1.0 and a.stuck_counter == b_.stuck_counter == 0
         assert len(a.residual_history) == len(b_.residual_history) and len(a.param_history) == len(b_.param_history)
+
+
+def test_generation_with_device_dedup_equals_generation_without():
+    """dedup.gpu_generation_dedup is gpu_generation with the similarity tests answered from the Gram matrix: every
+    generation of a run must leave the same population behind."""
+    from adaptive_matrix_solver_b200.population import gpu_generation
+    from adaptive_matrix_solver_b200.dedup import gpu_generation_dedup
+    from fake_engine import FakeEngine
+    ams = load_reference(gmres_shim=True, name="ams_dropin_d")
+    a, b_ = _build(ams, 16, 12, 3), _build(ams, 16, 12, 3)
+    ea, eb = FakeEngine(), FakeEngine()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for it in range(1, 29):
+            np.random.seed(100 + it); random.seed(100 + it)
+            quiet(gpu_generation, a, it, ea)
+            np.random.seed(100 + it); random.seed(100 + it)
+            quiet(gpu_generation_dedup, ams, b_, it, eb)
+            assert len(a.candidates) == len(b_.candidates)
+            assert [c.state for c in a.candidates] == [c.state for c in b_.candidates]
+            assert a.num_distinct_converged_solutions == b_.num_distinct_converged_solutions
+    assert a.num_distinct_converged_solutions >= 1
+    for ca, cb in zip(a.candidates, b_.candidates):
+        assert ca.lambda_k == cb.lambda_k and np.array_equal(ca.v_k, cb.v_k)
