@@ -342,11 +342,11 @@ __global__ void __launch_bounds__(256) lu_permute_rows_kernel(cplx* W, long long
 // streamed through a ring of TRTRI_PF row buffers with cp.async so the global-load latency of row r + TRTRI_PF - 1
 // hides behind the arithmetic of rows r .. r + TRTRI_PF - 2 (the one-row-ahead version was latency-bound: 353 us).
 //
-// The row recurrence is sequential (two CTA barriers per row), so the block is split in two halves of h = jb / 2 rows:
-//   phase A  inverts the two diagonal blocks X11, X22 SIMULTANEOUSLY (threads c < h work on row rl, threads c >= h on row
-//            h + rl of the same iteration): h - 1 instead of jb - 1 sequential steps;
-//   phase B  X21 = -X22 (L21 X11): two h x h x h triangular products spread over all threads (T = L21 X11 goes into X21's
-//            slots, then X21 row by row from the bottom up, in place).
+// The row recurrence is sequential (two CTA barriers per row), so the block is split into 4 (or 2) diagonal blocks of h rows:
+//   phase A  inverts all diagonal blocks SIMULTANEOUSLY (thread column c works on row rl of its own block in the same
+//            iteration): h - 1 instead of jb - 1 sequential steps;
+//   phase B  fills the off-diagonal blocks level by level, X21 = -X22 (L21 X11): triangular block products spread over the
+//            threads (T = L21 X11 goes into X21's slots, then X21 row by row from the bottom up, in place).
 constexpr int TRTRI_PF = 8;
 constexpr int TRTRI_SPLIT = 4;     // lanes sharing one column's dot product (critical path / 4)
 __global__ void __launch_bounds__(LU_NB * TRTRI_SPLIT) lu_trtri_kernel(const cplx* __restrict__ W, long long strideW, int n, int k0,
@@ -356,10 +356,12 @@ __global__ void __launch_bounds__(LU_NB * TRTRI_SPLIT) lu_trtri_kernel(const cpl
     cplx* rowbuf = X + (LU_NB * (LU_NB + 1)) / 2;                  // TRTRI_PF x LU_NB ring of rows of L
     const int b = blockIdx.x, c = threadIdx.x / TRTRI_SPLIT, sp = threadIdx.x % TRTRI_SPLIT;
     const cplx* L = W + (long long)b * strideW + (long long)k0 * n + k0;   // L[r + p*n]
-    const int h = (jb >= 32 && (jb & 1) == 0) ? jb / 2 : jb;       // half size (h == jb: one block, no phase B)
-    const int base = (c >= h) ? h : 0;                             // first row / column of this thread's diagonal block
+    // diagonal blocks inverted simultaneously: 4 (jb a multiple of 4, >= 64), 2 (jb even, >= 32) or 1
+    const int nblk = (jb >= 64 && (jb & 3) == 0) ? 4 : ((jb >= 32 && (jb & 1) == 0) ? 2 : 1);
+    const int h = jb / nblk;                                       // diagonal block size
+    const int base = (c < jb) ? (c / h) * h : jb;                  // first row / column of this thread's diagonal block
     if (c < jb && sp == 0) X[(c * (c + 1)) / 2 + c] = cmake(1.0, 0.0);
-    // ring slot entry c holds L[base + rl][c]: the top block's row rl for c < h, the bottom block's row h + rl for c >= h
+    // ring slot entry c holds L[base + rl][c]: row rl of the diagonal block that column c belongs to
     auto fetch_row = [&](int rl) {
         const int r = base + rl;
         if (rl < h && r < jb && c < r && sp == 0) {
@@ -387,39 +389,54 @@ __global__ void __launch_bounds__(LU_NB * TRTRI_SPLIT) lu_trtri_kernel(const cpl
         }
         __syncthreads();       // X row complete; ring slot rl % PF may be refilled by the next fetch
     }
-    if (h < jb) {
-        // ---- phase B: X21 = -X22 * (L21 * X11) ----
-        // T[i][j] = sum_{p = j}^{h-1} L21[i][p] X11[p][j]  -> slot of X21[i][j]; thread t: i = t % h, columns j = t / h + u * (NT / h)
-        const int NT = LU_NB * TRTRI_SPLIT;
-        {
-            const int i = threadIdx.x % h;
-            const cplx* l21 = L + (h + i);                         // L21[i][p] = l21[p * n] (consecutive threads, consecutive rows)
-            for (int j = threadIdx.x / h; j < h; j += NT / h) {
+    // ---- phase B: off-diagonal blocks, level by level: X21 = -X22 * (L21 * X11) for the pair of hh x hh blocks at offset o ----
+    // executed by the nt threads [t0, t0 + nt) (warp-aligned); both __syncthreads are reached by every thread of the CTA
+    auto pair_product = [&](int o, int hh, int t0, int nt) {
+        const int tl = (int)threadIdx.x - t0;
+        const bool mine = tl >= 0 && tl < nt;
+        // T[i][j] = sum_{p = j}^{hh-1} L21[i][p] X11[p][j]  -> slot of X21[i][j]; thread tl: row i = tl % hh, columns j = tl / hh + u * (nt / hh)
+        if (mine) {
+            const int i = tl % hh;
+            const cplx* l21 = L + (o + hh + i) + (long long)o * n;     // L21[i][p] = l21[p * n] (consecutive threads, consecutive rows)
+            for (int j = tl / hh; j < hh; j += nt / hh) {
                 cplx acc = cmake(0.0, 0.0);
-                for (int p = j; p < h; ++p) cfma(acc, __ldg(&l21[(long long)p * n]), X[(p * (p + 1)) / 2 + j]);
-                X[((h + i) * (h + i + 1)) / 2 + j] = acc;
+                for (int p = j; p < hh; ++p) cfma(acc, __ldg(&l21[(long long)p * n]), X[((o + p) * (o + p + 1)) / 2 + o + j]);
+                X[((o + hh + i) * (o + hh + i + 1)) / 2 + o + j] = acc;
             }
         }
         __syncthreads();
         // X21[i][j] = -sum_{q <= i} X22[i][q] T[q][j], rows from the bottom up so that T[q <= i][j] is still intact; column j
         // is owned by a group of 8 lanes (dot product split over them)
         {
-            const int j = threadIdx.x >> 3, l8 = threadIdx.x & 7;
-            for (int i = h - 1; i >= 0; --i) {
+            const int j = tl >> 3, l8 = tl & 7;
+            const bool col = mine && j < hh;
+            for (int i = hh - 1; i >= 0; --i) {
                 cplx acc = cmake(0.0, 0.0);
-                if (j < h) {
-                    const cplx* x22 = X + ((h + i) * (h + i + 1)) / 2 + h;       // X22[i][q], q <= i
-                    for (int q = l8; q <= i; q += 8) cfma(acc, x22[q], X[((h + q) * (h + q + 1)) / 2 + j]);
+                const int ri = o + hh + i;
+                if (col) {
+                    const cplx* x22 = X + (ri * (ri + 1)) / 2 + o + hh;          // X22[i][q], q <= i
+                    for (int q = l8; q <= i; q += 8) cfma(acc, x22[q], X[((o + hh + q) * (o + hh + q + 1)) / 2 + o + j]);
                 }
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) {
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                for (int s8 = 4; s8 > 0; s8 >>= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s8); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s8);
                 }
-                if (j < h && l8 == 0) X[((h + i) * (h + i + 1)) / 2 + j] = cmake(-acc.x, -acc.y);
+                if (col && l8 == 0) X[(ri * (ri + 1)) / 2 + o + j] = cmake(-acc.x, -acc.y);
                 __syncwarp();
             }
         }
         __syncthreads();
+    };
+    {
+        const int NT = LU_NB * TRTRI_SPLIT;
+        if (nblk == 4) {
+            // level 1: the two pairs of h-blocks side by side (half of the CTA each), level 2: the pair of 2h-blocks
+            const int upper = ((int)threadIdx.x < NT / 2) ? 0 : 1;        // one call site: every thread passes the same barriers
+            pair_product(upper * 2 * h, h, upper * (NT / 2), NT / 2);
+            pair_product(0, 2 * h, 0, NT);
+        } else if (nblk == 2) {
+            pair_product(0, h, 0, NT);
+        }
     }
     cplx* out = Linv + (long long)b * LU_NB * LU_NB;
     for (int r = sp; r < jb; r += TRTRI_SPLIT)
