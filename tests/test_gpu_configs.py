@@ -99,3 +99,32 @@ def test_direct_solve_at_the_maximum_order(eng):
         r = A @ X[c] - (lam[c] - psi[c]) * X[c] - V[c]
         be = np.linalg.norm(r) / (anorm * np.linalg.norm(X[c]) + np.linalg.norm(V[c]))
         assert be < 1e-13, be
+
+
+@pytest.mark.timeout(600)
+def test_k4_population_step_through_seam_b_full_size(eng):
+    """Config 4 through the drop-in boundary (step_population on candidate objects, GMRES preferred, Jacobi for the stuck
+    half, AMS:61-90, 284-285, 298-299): x <- (1 - a) x + a x_solve with x_solve meeting scipy's rtol, residual = ||A x - b||."""
+    import random
+    from adaptive_matrix_solver_b200 import step_population
+    from adaptive_matrix_solver_b200.workloads import k4_system
+    from mock_candidate import MockCandidate, ProblemType
+    n, C = 8192, 8
+    A, b = k4_system(n)
+    np.random.seed(4); random.seed(4)
+    cands = [MockCandidate(A, ProblemType.SOLVE_LINEAR_SYSTEM, n) for _ in range(C)]
+    for k, c in enumerate(cands):
+        c.stuck_counter = 2 if k % 2 else 0                      # > 1 switches the Jacobi preconditioner on (AMS:64)
+        c.alpha_local_step = 0.25
+    x_before = [c.x_k.copy() for c in cands]
+    strat = dict(overall_psi_aggression_factor=10.0, max_psi_retries=25, current_convergence_threshold=1e-4)
+    know = dict(local_solver_preference="gmres", is_sparse_problem=False, is_hermitian=False)
+    assert step_population(cands, A, b, strat, know, eng) == C
+    nb = np.linalg.norm(b)
+    for c, x0 in zip(cands, x_before):
+        assert c.local_psi_retries_needed == 0                   # first attempt succeeded: GMRES converged for every candidate
+        xs = (c.x_k - 0.75 * x0) / 0.25                          # the solve result behind the damped mix (AMS:285)
+        assert np.linalg.norm(A @ xs - b) <= 2e-8 * nb
+        r = np.linalg.norm(A @ c.x_k - b)
+        assert abs(c.residual_k - r) <= 1e-10 * max(r, 1.0)
+    assert [c.stuck_counter for c in cands] == [0, 1] * (C // 2)  # max(0, stuck - 1) on success (AMS:286)
