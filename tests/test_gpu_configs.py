@@ -118,7 +118,7 @@ def test_k4_population_step_through_seam_b_full_size(eng):
         c.alpha_local_step = 0.25
     x_before = [c.x_k.copy() for c in cands]
     strat = dict(overall_psi_aggression_factor=10.0, max_psi_retries=25, current_convergence_threshold=1e-4)
-    know = dict(local_solver_preference="gmres", is_sparse_problem=False, is_hermitian=False)
+    know = dict(local_solver_preference="iterative_gmres", is_sparse_problem=False, is_hermitian=False)
     assert step_population(cands, A, b, strat, know, eng) == C
     nb = np.linalg.norm(b)
     for c, x0 in zip(cands, x_before):
@@ -128,3 +128,32 @@ def test_k4_population_step_through_seam_b_full_size(eng):
         r = np.linalg.norm(A @ c.x_k - b)
         assert abs(c.residual_k - r) <= 1e-10 * max(r, 1.0)
     assert [c.stuck_counter for c in cands] == [0, 1] * (C // 2)  # max(0, stuck - 1) on success (AMS:286)
+
+
+@pytest.mark.timeout(900)
+def test_k5_sparse_population_step_through_seam_b_full_size(eng):
+    """Config 5 through the drop-in boundary: sparse CSC linear system, n = 1 000 000, GMRES / SpMV path, long-vector mix and
+    residual kernels (AMS:46-47, 61-90, 285, 299)."""
+    import random
+    from adaptive_matrix_solver_b200 import step_population
+    from adaptive_matrix_solver_b200.workloads import k5_sparse
+    from mock_candidate import MockCandidate, ProblemType
+    n, C = 1_000_000, 3
+    A = k5_sparse(n)
+    rng = np.random.default_rng(8)
+    b = rng.random(n) + 1j * rng.random(n)
+    np.random.seed(6); random.seed(6)
+    cands = [MockCandidate(A, ProblemType.SOLVE_LINEAR_SYSTEM, n) for _ in range(C)]
+    for c in cands:
+        c.alpha_local_step = 0.5
+    x_before = [c.x_k.copy() for c in cands]
+    strat = dict(overall_psi_aggression_factor=1.0, max_psi_retries=25, current_convergence_threshold=1e-6)
+    know = dict(local_solver_preference="iterative_gmres", is_sparse_problem=True, is_hermitian=False)
+    assert step_population(cands, A, b, strat, know, eng) == C
+    nb = np.linalg.norm(b)
+    for c, x0 in zip(cands, x_before):
+        assert c.local_psi_retries_needed == 0
+        xs = 2.0 * c.x_k - x0                                    # the solve result behind the damped mix (alpha = 0.5)
+        assert np.linalg.norm(A @ xs - b) <= 2e-8 * nb
+        r = np.linalg.norm(A @ c.x_k - b)
+        assert abs(c.residual_k - r) <= 1e-10 * max(r, 1.0)
