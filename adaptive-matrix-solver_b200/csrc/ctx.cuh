@@ -85,7 +85,15 @@ cudaError_t maus_dev_alloc(maus_ctx* ctx, void** p, size_t bytes);
 void maus_dev_free(maus_ctx* ctx, void* p, size_t bytes);
 int maus_ensure_population(maus_ctx* ctx, long long C);
 
-// profiling brackets (no-ops unless enabled)
+// NVTX ranges (kernel families; no-ops without an attached tool)
+void maus_nvtx_push(const char* name);
+void maus_nvtx_pop();
+struct MausNvtxRange {
+    explicit MausNvtxRange(const char* name) { maus_nvtx_push(name); }
+    ~MausNvtxRange() { maus_nvtx_pop(); }
+};
+
+// profiling brackets (event timing is a no-op unless enabled; each pair is also an NVTX range)
 int prof_begin(maus_ctx* ctx, int kind, double work);
 void prof_end(maus_ctx* ctx, int handle);
 void prof_tag(maus_ctx* ctx, int handle, int M, int N, int K, int batch);

@@ -526,6 +526,9 @@ static int gmres_ensure(maus_ctx* ctx, long long n, long long C, GmresWs** out) 
     GM_ALLOC(ws->jacbad, (size_t)ws->C * sizeof(int));
     GM_ALLOC(ws->red, (size_t)ws->C * sizeof(cplx));
     GM_ALLOC(ws->active_idx, (size_t)ws->C * sizeof(int));
+    // compaction buffers are part of the workspace: allocating them lazily could fail on ONE rank of a row-sharded solve
+    // and make the ranks issue different numbers of collectives
+    GM_ALLOC(ws->vc, vec); GM_ALLOC(ws->zc, vec);
 #undef GM_ALLOC
     ws->bytes = total;
     ctx->bytes_held += (long long)total;
@@ -541,6 +544,7 @@ int gmres_core(maus_ctx* ctx, const GmresOperator& op, long long C, const cplx* 
                int* status, int* iters, double max_psi_host) {
     GmresWs* ws = nullptr;
     const long long n = op.nloc;
+    MausNvtxRange nvtx_range("maus.gmres");
     int rc = gmres_ensure(ctx, n, C, &ws); if (rc) return rc;
     // restart = min(20, GLOBAL order) (scipy), not the local slice length
     ws->m = (int)std::min<long long>(GM_RESTART, std::min<long long>(op.nglobal, ws->m_cap));
@@ -647,17 +651,9 @@ int gmres_core(maus_ctx* ctx, const GmresOperator& op, long long C, const cplx* 
         n_active = host_counters[1];
         // compaction pays once a quarter of the batch has finished (and changes the passes of 4 of the SpMM / the GEMM width)
         if (n_active > 0 && n_active * 4 <= C * 3 && n_active != n_compact) {
-            if (!ws->vc) {
-                const size_t vec = (size_t)ws->C * n * sizeof(cplx);
-                if (cudaMalloc((void**)&ws->vc, vec) != cudaSuccess || cudaMalloc((void**)&ws->zc, vec) != cudaSuccess) {
-                    cudaFree(ws->vc); ws->vc = nullptr; cudaGetLastError();          // no memory: keep the full-width matvec
-                } else { ws->bytes += 2 * vec; ctx->bytes_held += (long long)(2 * vec); }
-            }
-            if (ws->vc) {
-                gm_list_active_kernel<<<1, 1, 0, st>>>(ws->cand, (int)C, ws->active_idx);
-                ctx->launches += 1;
-                n_compact = n_active;
-            }
+            gm_list_active_kernel<<<1, 1, 0, st>>>(ws->cand, (int)C, ws->active_idx);
+            ctx->launches += 1;
+            n_compact = n_active;
         }
     }
     gm_finish_kernel<<<gridv, GM_NT, 0, st>>>(ws->cand, ws->x, n, X, status, iters, nblk);

@@ -5,6 +5,7 @@
 #include <new>
 #include <algorithm>
 #include <functional>
+#include <nvtx3/nvToolsExt.h>
 #include "ctx.cuh"
 #include "vec.cuh"
 #include "spmv.cuh"
@@ -53,8 +54,17 @@ void prof_tag(maus_ctx* ctx, int h, int M, int N, int K, int batch) {
 
 static int lu_use_3m();
 
+// NVTX range per kernel family: visible in nsys / ncu --nvtx timelines, a no-op (one pointer test in
+// the header-only NVTX3 loader) when no tool is attached.  Every prof_begin / prof_end pair is also a range.
+static const char* const k_prof_names[MAUS_PROF_KINDS] = {"maus.lu.gemm", "maus.matvec", "maus.lu.panel", "maus.lu.trtri",
+                                                          "maus.lu.backsolve", "maus.lu.build", "maus.lu.permute",
+                                                          "maus.matvec.gemm", "maus.vec"};
+void maus_nvtx_push(const char* name) { nvtxRangePushA(name); }
+void maus_nvtx_pop() { nvtxRangePop(); }
+
 int prof_begin(maus_ctx* ctx, int kind, double work) {
     ProfAccum& pr = ctx->prof;
+    nvtxRangePushA(k_prof_names[kind]);
     if (!pr.enabled) return -1;
     if (pr.used + 2 > pr.ev.size()) {
         cudaStreamSynchronize(ctx->stream);
@@ -74,6 +84,7 @@ int prof_begin(maus_ctx* ctx, int kind, double work) {
     return h;
 }
 void prof_end(maus_ctx* ctx, int h) {
+    nvtxRangePop();
     if (h < 0) return;
     cudaEventRecord(ctx->prof.ev[h + 1], ctx->stream);
 }
@@ -107,7 +118,6 @@ int maus_ensure_population(maus_ctx* ctx, long long C) {
     const long long n = ctx->n, oldC = ctx->Ccap;
     cplx* oldV = ctx->V;
     ctx->V = nullptr;                      // detach so free_population leaves it alone
-    if (oldV) ctx->bytes_held += 0;
     free_population(ctx);
     const long long cap = std::max<long long>(C, 8);
     int rc;
@@ -821,32 +831,67 @@ extern "C" int maus_gram(maus_ctx* ctx, int64_t C, int64_t n, const double* V, d
     return MAUS_OK;
 }
 
+// device buffers of one call, released on every exit path
+namespace {
+struct ScratchBufs {
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    int used = 0;
+    cudaError_t alloc(void** out, size_t bytes) {
+        cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+        if (e == cudaSuccess && used < 4) p[used++] = *out;
+        return e;
+    }
+    ~ScratchBufs() { for (int i = 0; i < used; ++i) cudaFree(p[i]); }
+};
+}  // namespace
+
+static int zgemm_host(maus_ctx* ctx, const char* who, int M, int N, int K, int batch, const double* A, const double* B, double* Cm,
+                      int beta, int negate, int algo /*0 FMA, 1 DMMA 4-product, 2 DMMA 3M*/) {
+    cudaSetDevice(ctx->device);
+    ScratchBufs bufs;
+    cplx *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    const size_t ba = (size_t)M * K * batch * sizeof(cplx), bb = (size_t)K * N * batch * sizeof(cplx),
+                 bc = (size_t)M * N * batch * sizeof(cplx);
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = bufs.alloc((void**)&dA, ba);
+    if (e == cudaSuccess) e = bufs.alloc((void**)&dB, bb);
+    if (e == cudaSuccess) e = bufs.alloc((void**)&dC, bc);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dA, A, ba, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dB, B, bb, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && beta) e = cudaMemcpyAsync(dC, Cm, bc, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        ZgemmParams p = {};
+        p.A = dA; p.lda = M; p.strideA = (long long)M * K;
+        p.B = dB; p.ldb = K; p.strideB = (long long)K * N;
+        p.C = dC; p.ldc = M; p.strideC = (long long)M * N;
+        p.M = M; p.N = N; p.K = K; p.batch = batch; p.beta = beta; p.negate = negate;
+        p.algo3m = (algo == 2) ? 1 : 0;                     // 2: the three-product (3M) tensor-pipe kernel of the LU updates
+        e = algo ? zgemm_dmma_launch(p, st) : zgemm_simple_launch(p, st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Cm, dC, bc, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = e2;
+    ctx->launches += 1;
+    if (e != cudaSuccess) return maus_fail(ctx, MAUS_E_CUDA, who, e);
+    return MAUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Hermitian shortcut: similarity scores of all candidates against all eigenvectors (AMS:165) as one tensor-pipe GEMM
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int maus_project(maus_ctx* ctx, int64_t n, int64_t m, const double* Ec, int64_t C, const double* V, double* P_out) {
+    if (!ctx || !Ec || !V || !P_out || n <= 0 || m <= 0 || C <= 0 || n > 0x7fffffffLL || m > 0x7fffffffLL || C > 0x7fffffffLL)
+        return maus_fail(ctx, MAUS_E_ARG, "maus_project: bad argument");
+    // Ec [n][m] in C order is E^H (m x n) column-major; V [C][n] is the n x C column-major block of the candidates;
+    // P [C][m] is E^H V column-major
+    return zgemm_host(ctx, "maus_project", (int)m, (int)C, (int)n, 1, Ec, V, P_out, 0, 0, 1);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // debug / parity hooks
 // ------------------------------------------------------------------------------------------------------------
 extern "C" int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, const double* A, const double* B, double* Cm,
                                 int beta, int negate, int use_dmma) {
     if (!ctx || !A || !B || !Cm || M <= 0 || N <= 0 || K <= 0 || batch <= 0) return maus_fail(ctx, MAUS_E_ARG, "maus_debug_zgemm");
-    cudaSetDevice(ctx->device);
-    cplx *dA = nullptr, *dB = nullptr, *dC = nullptr;
-    const size_t ba = (size_t)M * K * batch * sizeof(cplx), bb = (size_t)K * N * batch * sizeof(cplx),
-                 bc = (size_t)M * N * batch * sizeof(cplx);
-    MAUS_CUDA(ctx, cudaMalloc(&dA, ba)); MAUS_CUDA(ctx, cudaMalloc(&dB, bb)); MAUS_CUDA(ctx, cudaMalloc(&dC, bc));
-    cudaStream_t st = ctx->stream;
-    MAUS_CUDA(ctx, cudaMemcpyAsync(dA, A, ba, cudaMemcpyHostToDevice, st));
-    MAUS_CUDA(ctx, cudaMemcpyAsync(dB, B, bb, cudaMemcpyHostToDevice, st));
-    MAUS_CUDA(ctx, cudaMemcpyAsync(dC, Cm, bc, cudaMemcpyHostToDevice, st));
-    ZgemmParams p = {};
-    p.A = dA; p.lda = M; p.strideA = (long long)M * K;
-    p.B = dB; p.ldb = K; p.strideB = (long long)K * N;
-    p.C = dC; p.ldc = M; p.strideC = (long long)M * N;
-    p.M = M; p.N = N; p.K = K; p.batch = batch; p.beta = beta; p.negate = negate;
-    p.algo3m = (use_dmma == 2) ? 1 : 0;                     // 2: the three-product (3M) tensor-pipe kernel of the LU updates
-    cudaError_t e = use_dmma ? zgemm_dmma_launch(p, st) : zgemm_simple_launch(p, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(Cm, dC, bc, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(dA); cudaFree(dB); cudaFree(dC);
-    ctx->launches += 1;
-    if (e != cudaSuccess) return maus_fail(ctx, MAUS_E_CUDA, "maus_debug_zgemm", e);
-    return MAUS_OK;
+    return zgemm_host(ctx, "maus_debug_zgemm", M, N, K, batch, A, B, Cm, beta, negate, use_dmma);
 }

@@ -140,6 +140,9 @@ static int rs_ensure(maus_ctx* ctx, RowShard* rs, long long C) {
     MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(rs->xfull); cudaFree(rs->pack); cudaFree(rs->V); cudaFree(rs->X); cudaFree(rs->Y); cudaFree(rs->sigma); cudaFree(rs->psi);
     cudaFree(rs->jac); cudaFree(rs->status); cudaFree(rs->iters);
+    // a failing cudaMalloc below returns early: no pointer may stay dangling for maus_rowshard_free
+    rs->xfull = rs->pack = rs->V = rs->X = rs->Y = rs->sigma = nullptr; rs->psi = nullptr; rs->jac = nullptr;
+    rs->status = rs->iters = nullptr; rs->Ccap = 0;
     const long long cap = std::max<long long>(C, 4);
     MAUS_CUDA(ctx, cudaMalloc(&rs->xfull, (size_t)cap * rs->n * sizeof(cplx)));
     MAUS_CUDA(ctx, cudaMalloc(&rs->pack, (size_t)4 * rs->n * sizeof(cplx)));

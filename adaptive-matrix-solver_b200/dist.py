@@ -15,7 +15,7 @@ from .population import step_population
 
 # float64 record per candidate exchanged each generation
 REC_FIELDS = ("lambda_re", "lambda_im", "residual", "prev_residual", "alpha_re", "alpha_is_complex", "stuck", "retries",
-              "resets", "w", "state", "hist_added")
+              "resets", "w", "state", "hist_added", "lambda_is_real", "rng_drawn")
 NREC = len(REC_FIELDS)
 
 
@@ -63,23 +63,40 @@ class Shard:
         self._dist().all_reduce(t, op=self._dist().ReduceOp.MAX)
         return float(t.item())
 
+    def all_reduce_sum(self, value):
+        import torch
+        if self.world == 1:
+            return float(value)
+        t = torch.tensor([float(value)], dtype=torch.float64, device=self.device if self.device is not None else "cpu")
+        self._dist().all_reduce(t, op=self._dist().ReduceOp.SUM)
+        return float(t.item())
+
     def barrier(self):
         if self.world > 1:
             self._dist().barrier()
 
 
-def _record(c, hist_before):
+def _rng_fingerprint():
+    """cheap identity of the two global host RNG streams the reference draws re-initialisations from (AMS:130-135, 260, 283)"""
+    import random
+    st = np.random.get_state()
+    return (int(st[2]), int(st[1][0]), int(st[1][-1]), hash(random.getstate()[1][-3:]))
+
+
+def _record(c, hist_before, rng_drawn=False):
     al = c.alpha_local_step
     lam = complex(c.lambda_k) if c.lambda_k is not None else complex(0.0, 0.0)
+    lam_real = c.lambda_k is not None and not isinstance(c.lambda_k, (complex, np.complexfloating))
     return [lam.real, lam.imag, float(c.residual_k), float(c.prev_residual), complex(al).real,
             1.0 if isinstance(al, (complex, np.complexfloating)) else 0.0, float(c.stuck_counter),
             float(c.local_psi_retries_needed), float(c.num_resets), float(c.w_k), float(c.state.value),
-            float(len(c.residual_history) - hist_before)]
+            float(len(c.residual_history) - hist_before), 1.0 if lam_real else 0.0, 1.0 if rng_drawn else 0.0]
 
 
 def _apply_record(c, rec, vec, eigen, State):
     if eigen:
-        c.lambda_k = np.complex128(complex(rec[0], rec[1]))
+        # the Hermitian shortcut stores a real float64 eigenvalue (AMS:171), the inverse-iteration branch a complex128
+        c.lambda_k = np.float64(rec[0]) if rec[12] else np.complex128(complex(rec[0], rec[1]))
         c.v_k = vec
     else:
         c.x_k = vec
@@ -115,12 +132,14 @@ def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, e
     counts = [len(range(r, len(live), shard.world)) for r in range(shard.world)]
     mine = [live[i] for i in shard.owned(len(live))]
     hist_before = [len(c.residual_history) for c in mine]
+    rng_before = _rng_fingerprint()
     if mine:
         step_population(mine, M, b, strat_params, problem_knowledge, engine)
+    rng_drawn = _rng_fingerprint() != rng_before
     # record + vector travel together as one float64 row: [NREC | 2n]
     local = np.zeros((len(mine), NREC + 2 * n), dtype=np.float64)
     for k, c in enumerate(mine):
-        local[k, :NREC] = _record(c, hist_before[k])
+        local[k, :NREC] = _record(c, hist_before[k], rng_drawn)
         vec = c.v_k if eigen else c.x_k
         local[k, NREC:] = np.ascontiguousarray(vec, dtype=np.complex128).view(np.float64)
     gathered = shard.all_gather_rows(local, max(counts))
@@ -131,7 +150,27 @@ def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, e
             row = gathered[r][k]
             vec = row[NREC:].copy().view(np.complex128)
             _apply_record(live[i], row[:NREC], vec, eigen, State)
+    _resync_host_rng(gathered, counts)
     return len(live)
+
+
+def _resync_host_rng(gathered, counts):
+    """Re-initialisations (AMS:260, 283, 293) draw from the OWNING rank's global numpy / random streams only, so after the first
+    failure or collapse the replicas' streams differ and the reference's ``_manage_candidates`` (AMS:525-549: ``random.choice``,
+    ``np.random.rand``) would spawn different candidates per rank.  When any rank drew this generation, every rank re-seeds
+    both streams from a digest of the gathered records -- data all ranks hold bit-identically -- so the replicas stay equal."""
+    drew = any(counts[r] and gathered[r][:counts[r], REC_FIELDS.index("rng_drawn")].any() for r in range(len(gathered)))
+    if not drew:
+        return False
+    import hashlib
+    import random
+    h = hashlib.sha256()
+    for r in range(len(gathered)):
+        h.update(np.ascontiguousarray(gathered[r][:counts[r], :NREC]).tobytes())
+    seed = int.from_bytes(h.digest()[:8], "little")
+    np.random.seed(seed % (2 ** 32))
+    random.seed(seed)
+    return True
 
 
 def gather_energy_and_best(shard, resid, lam, vectors, best_index=None):

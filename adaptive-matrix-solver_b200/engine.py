@@ -40,6 +40,7 @@ class MausEngine:
         self.n = 0
         self.is_sparse = False
         self.generation = 0
+        self.matrix_epoch = [0, 0]          # uploads per slot; population._MatrixCache compares it (shared-engine safety)
         self._pinned = []
         if workspace_limit_bytes:
             self._check(self._lib.maus_set_workspace_limit(self._h, int(workspace_limit_bytes)))
@@ -149,6 +150,8 @@ class MausEngine:
                 self.is_sparse = False
         if slot == _abi.SLOT_CURRENT:
             self.n = n
+            self.matrix_epoch[1] += 1       # a new slot-0 matrix may change n, which drops slot 1 on the device
+        self.matrix_epoch[slot] += 1
 
     def set_rhs(self, b):
         b = _as_c128(b, (self.n,))
@@ -255,8 +258,9 @@ class MausEngine:
         n, m = Ec.shape
         if V.ndim != 2 or V.shape[1] != n:
             raise ValueError("V must be [C][n]")
-        out = np.zeros((1, V.shape[0], m), dtype=_c128)
-        return self.debug_zgemm(Ec[None], V[None], out, beta=0, negate=False, use_dmma=1)[0]
+        out = np.empty((V.shape[0], m), dtype=_c128)
+        self._check(self._lib.maus_project(self._h, n, m, _dp(Ec), V.shape[0], _dp(V), _dp(out)))
+        return out
 
     def gram(self, V):
         """G[i][j] = np.vdot(V[i], V[j]) for the rows of V ([C][n] complex128) in one device pass (dedup similarity tests)."""

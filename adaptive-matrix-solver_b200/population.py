@@ -43,9 +43,13 @@ class _MatrixCache:
     def __init__(self):
         self.obj = [None, None]
         self.form = [None, None]
+        self.epoch = [None, None]
 
     def ensure(self, engine, A, slot, form):
-        if self.obj[slot] is A and self.form[slot] == form:
+        # the engine counts every upload per slot (``matrix_epoch``): a Seam-A solve or any other direct ``set_matrix`` on the
+        # shared engine between two generations (AMS:224 pass-through candidates) invalidates what this cache believes is resident
+        epoch = getattr(engine, "matrix_epoch", None)
+        if self.obj[slot] is A and self.form[slot] == form and (epoch is None or self.epoch[slot] == epoch[slot]):
             return
         if form == 'dense' and _is_sparse(A):
             engine.set_matrix(A.toarray(), slot)
@@ -53,6 +57,8 @@ class _MatrixCache:
             engine.set_matrix(A, slot)
         self.obj[slot] = A
         self.form[slot] = form
+        epoch = getattr(engine, "matrix_epoch", None)
+        self.epoch[slot] = None if epoch is None else epoch[slot]
         if slot == 0:
             self.obj[1] = None      # n may have changed; slot 1 is re-uploaded on demand
 
@@ -74,8 +80,8 @@ def _ladder(engine, ptype, v_or_x, lam, stuck, base_psi, max_attempts, pref, mat
             psi = psi_magnitude(base_psi, attempts, stuck)
             key = None if matrix_sparse_semantics else [_key(cand_id, engine.generation, attempts + 1)]
             m = _METHOD.get(method)
-            if m is None or (m == _abi.METHOD_LU and engine.is_sparse):
-                status = _abi.ST_ZERO_PIVOT
+            if m is None or (m == _abi.METHOD_LU and (engine.is_sparse or engine.n > LU_MAX_N)):
+                status = _abi.ST_ZERO_PIVOT      # no direct solver for this operator on the device: the try fails (AMS:98)
                 X = None
             else:
                 X, st, _ = engine.solve_shifted([lam if ptype == _abi.EIGENVALUE else 0j], [complex(psi).real],
@@ -185,8 +191,8 @@ def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, 
     gen = engine.generation
     keys = None if is_sparse else np.array([_key(c.id, gen, 0) for c in cands], dtype=np.uint64)
     method0 = _METHOD.get(pref)
-    if method0 is None or (method0 == _abi.METHOD_LU and engine.is_sparse):
-        # unknown method / sparse-direct beyond the LU limit: the first try fails for everybody (AMS:92, 98)
+    if method0 is None or (method0 == _abi.METHOD_LU and (engine.is_sparse or N > LU_MAX_N)):
+        # unknown method / direct solve beyond the LU limit (sparse or dense): the first try fails for everybody (AMS:92, 98)
         out = dict(lam=engine.rq(V)[0] if eigen else np.zeros(C_, dtype=np.complex128),
                    resid=np.full(C_, np.inf), mixnorm=np.zeros(C_), status=np.full(C_, _abi.ST_ZERO_PIVOT, dtype=np.int32),
                    iters=np.zeros(C_, dtype=np.int32))
@@ -197,7 +203,8 @@ def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, 
 
     for i, c in enumerate(cands):
         st = int(status[i])
-        solved, retries, new_vec = (st == _abi.ST_OK), 0, None
+        # MIX_COLLAPSED = the solve succeeded but ||(1-a)v + a x|| <= 1e-10 (AMS:283): still the success branch
+        solved, retries = (st in (_abi.ST_OK, _abi.ST_MIX_COLLAPSED)), 0
         if eigen:
             c.lambda_k = np.complex128(lam[i])                                                  # AMS:268 (0 when |<v,v>| tiny)
         need_residual = False
@@ -281,9 +288,19 @@ def _step_group_svd(cands, M, b, strat_params, engine, State):
             if c.sigma_k < SIGMA_SIMILARITY_TOL_ABS / 100:                                      # AMS:243-247
                 c.state = State.CONVERGED
                 c.stuck_counter = 0
+                replaced = False
+                if np.linalg.norm(c.u_k) < 1e-10:                                               # AMS:246
+                    c.u_k = np.ones(Mr, dtype=np.complex128) / np.sqrt(Mr)
+                    replaced = True
+                if np.linalg.norm(c.right_v_k) < 1e-10:                                         # AMS:247
+                    c.right_v_k = np.ones(Mc, dtype=np.complex128) / np.sqrt(Mc)
+                    replaced = True
+                if replaced:
+                    redo.append(c)              # the device residual was taken on the un-replaced vectors (AMS:301 uses the new ones)
             else:
                 c.stuck_counter = max(0, c.stuck_counter - 1)                                   # AMS:248
-            c.residual_k = np.float64(out["resid"][i])                                          # AMS:301
+            if not (redo and redo[-1] is c):
+                c.residual_k = np.float64(out["resid"][i])                                      # AMS:301
         if failed:                                                                              # AMS:249-255
             c.stuck_counter += 1
             c.w_k *= 0.001

@@ -56,8 +56,8 @@ class GpuInverseIterateSolver:
             psi = psi_magnitude(self.base_psi_epsilon, num_psi_attempts, candidate_stuck_counter)
             status = None
             if method == 'direct_solve':
-                if sparse_in and A_target.shape[0] > LU_MAX_N:
-                    status = _abi.ST_ZERO_PIVOT      # no sparse direct solver on the device: behaves like a failed try
+                if A_target.shape[0] > LU_MAX_N:
+                    status = _abi.ST_ZERO_PIVOT      # beyond the batched LU (sparse or dense): behaves like a failed try
                 else:
                     if uploaded != 'dense':
                         eng.set_matrix(A_target.toarray() if sparse_in else A_target)

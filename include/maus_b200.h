@@ -159,6 +159,12 @@ int maus_svd_residual(maus_ctx* ctx, int64_t C, const double* U, const double* V
  * (Adaptive_Matrix_Solver_0.1.py:436, 450, 515, 520) by one device pass. */
 int maus_gram(maus_ctx* ctx, int64_t C, int64_t n, const double* V, double* G_out);
 
+/* ---- Hermitian shortcut --------------------------------------------------------------------------- */
+/* P[c][i] = <e_i, v_c> for the m eigenvectors E = [e_0 .. e_{m-1}] of sla.eigh and C candidate vectors: the similarity scores
+ * |v^H E| of Adaptive_Matrix_Solver_0.1.py:165 for the whole population as one tensor-pipe GEMM.  Ec = conj(E) in C order
+ * ([n][m] complex128), V [C][n], P_out [C][m]. */
+int maus_project(maus_ctx* ctx, int64_t n, int64_t m, const double* Ec, int64_t C, const double* V, double* P_out);
+
 /* ---- row-sharded sparse operator (BASELINE config 5 as worded) ---------------------------------- */
 /* Every rank owns n / world consecutive rows of A and the same slice of every vector; a matvec all-gathers its input,
  * GMRES all-reduces its dot products (NCCL over NVLink, bound at run time from `libpath` = the libnccl.so.2 the process

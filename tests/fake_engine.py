@@ -14,12 +14,23 @@ class FakeEngine:
         self.A = [None, None]
         self.b = None
         self.calls = 0
+        self.fail_ids = set()        # candidate ids whose every solve attempt fails (exercises the ladder + re-initialisation)
+        self.matrix_epoch = [0, 0]
 
     def set_matrix(self, A, slot=0):
         self.A[slot] = np.asarray(A, dtype=np.complex128)
         if slot == 0:
             self.n = self.A[0].shape[0]
             self.A[1] = None
+            self.matrix_epoch[1] += 1
+        self.matrix_epoch[slot] += 1
+
+    def upload_vectors(self, V):
+        pass
+
+    def solve_shifted(self, sigma, psi, rng_key=None, method=0, use_jacobi=None, RHS=None, rhs_shared=False, want_x=True):
+        C_ = len(sigma)          # only reached for candidates in fail_ids: every attempt of the ladder fails
+        return None, np.full(C_, 1, dtype=np.int32), np.zeros(C_, dtype=np.int32)
 
     def project(self, Ec, V):
         return (np.asarray(Ec).T @ np.asarray(V, dtype=np.complex128).T).T
@@ -42,6 +53,11 @@ class FakeEngine:
         lam = np.zeros(C_, dtype=np.complex128); resid = np.zeros(C_); mixn = np.zeros(C_)
         status = np.zeros(C_, dtype=np.int32); iters = np.zeros(C_, dtype=np.int32)
         for c in range(C_):
+            if rng_key is not None and (int(rng_key[c]) >> 32) in self.fail_ids:
+                if problem_type == 1:
+                    lam[c] = mo.rayleigh_quotient(A, V[c])
+                status[c] = 1
+                continue
             if problem_type == 1:
                 lam[c] = mo.rayleigh_quotient(A, V[c])
                 x = mo.shifted_solve_dense(A, lam[c], psi[c], V[c])

@@ -3,6 +3,7 @@ minutes per candidate here) plus one scipy cross-check where it is cheap.  K2 / 
 test_gpu_edges.py."""
 import numpy as np
 import pytest
+import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 pytestmark = pytest.mark.gpu
@@ -75,6 +76,13 @@ def test_k5_sparse_million_row_gmres_full_size(eng):
     assert (st == 0).all() and len(set(it.tolist())) == 1 and 1 <= it[0] <= 40
     for c in range(C):
         assert np.linalg.norm(A @ X[c] - V[c]) <= 1e-8 * (1 + 1e-6)          # ||b|| = 1
+    # scipy replay of candidate 0 on the same operator H = A + psi I (AMS:47-52), x0 = b (AMS:61, 89): the device GMRES must
+    # take exactly scipy's number of inner iterations and land on its solution
+    cnt = []
+    H = (A + 5e-19 * sp.identity(n, dtype=np.complex128, format="csc")).tocsr()
+    xr, info = spla.gmres(H, V[0], x0=V[0], rtol=1e-8, maxiter=50, callback=lambda r: cnt.append(r), callback_type="pr_norm")
+    assert info == 0 and len(cnt) == it[0], (len(cnt), it[0])
+    assert np.linalg.norm(X[0] - xr) <= 1e-7 * np.linalg.norm(xr)
 
 
 @pytest.mark.timeout(600)

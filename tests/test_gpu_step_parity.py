@@ -141,3 +141,113 @@ def test_seam_a_solver_signature_and_result(eng):
     bad = A.copy(); bad[0, 0] = np.nan
     with pytest.raises(RuntimeError):
         pkg.GpuInverseIterateSolver(n, mo.PSI_EPSILON_BASE, 3).solve(bad, b, 0)
+
+
+@pytest.mark.timeout(900)
+def test_benched_shape_k3_matches_oracle_two_generations(eng):
+    """The HEADLINE configuration (bench.py, BASELINE.json config 3 family): n = 4096 and a batch of 16 candidates, i.e. the
+    code path the benchmark times -- two-rows-per-thread panel clusters (batch >= 12), the K = 512 bulk trailing updates on
+    the 3M DMMA kernel, the batched A*V of the Rayleigh quotient / residual on the skinny 3M GEMM (C > 8).  Four of the 16
+    candidates are compared with the oracle (AMS:264-331 through mo.candidate_step, LAPACK zgesv) over two generations:
+    lambda, v up to phase, residual (floor 4e-13 ||A||), alpha bit-equal, state, stuck, retries."""
+    from adaptive_matrix_solver_b200 import step_population
+    from adaptive_matrix_solver_b200.workloads import k2_matrix, initial_vectors
+    n, C = 4096, 16
+    check = (0, 5, 10, 15)
+    A = k2_matrix(n, seed=20260)                                   # the matrix bench.py builds
+    V0 = initial_vectors(C, n, seed=20260)
+    np.random.seed(11); random.seed(11)
+    cands = []
+    for i in range(C):
+        c = MockCandidate(A, ProblemType.EIGENVALUE, n)
+        c.v_k = V0[i].copy(); c.lambda_k = 0j
+        cands.append(c)
+    strat = dict(overall_psi_aggression_factor=1.0, max_psi_retries=25, current_convergence_threshold=1e-10)
+    know = dict(local_solver_preference="direct_solve", is_sparse_problem=False, is_hermitian=False)
+    floor = 4e-13 * anorm(A)
+    oracles = {i: cands[i].to_oracle() for i in check}
+    prng = np.random.default_rng(5)                               # the oracle's Psi draws come from a private stream
+    for gen in range(2):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i in check:
+                mo.candidate_step(oracles[i], A, None, strat, know, rand=lambda *s: prng.random(s))
+        assert step_population(cands, A, None, strat, know, eng) == C
+        for i in check:
+            c, o = cands[i], oracles[i]
+            tag = f"gen {gen} cand {i}"
+            assert_scalar_close(c.lambda_k, o.lambda_k, floor, tag + " lambda")
+            assert_scalar_close(c.residual_k, o.residual_k, floor, tag + " residual")
+            assert vec_err_up_to_phase(c.v_k, o.v_k) <= 1e-9, tag
+            assert complex(c.alpha_local_step) == complex(o.alpha_local_step), tag
+            assert c.state.value == o.state and c.stuck_counter == o.stuck_counter, tag
+            assert c.local_psi_retries_needed == o.local_psi_retries_needed == 0, tag
+            assert len(c.residual_history) == o.history_len, tag
+    # every candidate of the batch (checked or not) satisfies the step's own invariants
+    for c in cands:
+        assert abs(np.linalg.norm(c.v_k) - 1.0) <= 1e-13
+        r = np.linalg.norm(A @ c.v_k - c.lambda_k * c.v_k)
+        assert abs(c.residual_k - r) <= 1e-10 * r + floor
+
+
+def test_forced_mix_collapse_takes_the_success_branch_like_the_oracle(eng):
+    """AMS:280-286: the solve succeeds but ||(1-a) v + a x|| <= 1e-10 (alpha = 1, a hugely scaled operator makes x tiny).  The
+    reference replaces v by rand/sqrt(N), KEEPS lambda, decrements stuck_counter and does not touch w / the state machine's
+    failure branch.  Both sides draw the replacement from the same global numpy state (the oracle's Psi draws use a private
+    stream here, the device draws none), so the new vector must be identical."""
+    from adaptive_matrix_solver_b200 import step_population
+    from adaptive_matrix_solver_b200.workloads import k2_matrix
+    n, C = 40, 3
+    A = 1e15 * k2_matrix(n, seed=7)
+    np.random.seed(21); random.seed(21)
+    cands = [MockCandidate(A, ProblemType.EIGENVALUE, n) for _ in range(C)]
+    for c in cands:
+        c.alpha_local_step = 1.0
+        c.stuck_counter = 3
+    cands[1].alpha_local_step = 0.25                               # this one does not collapse: (1-a) v keeps it O(1)
+    strat = dict(overall_psi_aggression_factor=1.0, max_psi_retries=25, current_convergence_threshold=1e-10)
+    know = dict(local_solver_preference="direct_solve", is_sparse_problem=False, is_hermitian=False)
+    oracles = [c.to_oracle() for c in cands]
+    prng = np.random.default_rng(0)
+    st_np, st_py = np.random.get_state(), random.getstate()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for o in oracles:
+            mo.candidate_step(o, A, None, strat, know, rand=lambda *s: prng.random(s))
+    np.random.set_state(st_np); random.setstate(st_py)
+    step_population(cands, A, None, strat, know, eng)
+    floor = 4e-13 * anorm(A)
+    for i, (c, o) in enumerate(zip(cands, oracles)):
+        assert c.stuck_counter == o.stuck_counter == 2, i             # success branch: max(0, stuck - 1)
+        assert c.w_k == o.w_k == 0.01 and c.num_resets == o.num_resets, i
+        assert c.state.value == o.state and complex(c.alpha_local_step) == complex(o.alpha_local_step), i
+        assert_scalar_close(c.lambda_k, o.lambda_k, floor, "lambda")
+        assert_scalar_close(c.residual_k, o.residual_k, floor, "residual")
+        if i != 1:
+            assert np.array_equal(c.v_k, o.v_k), i                    # same host draw on both sides, not normalised (AMS:283)
+            assert abs(np.linalg.norm(c.v_k) - 1.0) > 1e-3
+        else:
+            assert vec_err_up_to_phase(c.v_k, o.v_k) <= 1e-9
+
+
+@pytest.mark.timeout(600)
+def test_dense_order_beyond_the_lu_limit_falls_back_to_gmres(eng):
+    """A dense problem with n > 8192 and the reference's default preference 'direct_solve': the first try counts as failed and
+    the ladder switches to GMRES at attempt 0 (AMS:98-102) instead of aborting the generation."""
+    from adaptive_matrix_solver_b200 import step_population
+    n, C = 8320, 2
+    rng = np.random.default_rng(3)
+    A = (rng.random((n, n)) - 0.5 + 1j * (rng.random((n, n)) - 0.5)) / np.sqrt(n)
+    A[np.arange(n), np.arange(n)] += 6.0
+    b = A @ np.ones(n, dtype=np.complex128)
+    np.random.seed(2); random.seed(2)
+    cands = [MockCandidate(A, ProblemType.SOLVE_LINEAR_SYSTEM, n) for _ in range(C)]
+    for c in cands:
+        c.alpha_local_step = 1.0
+    strat = dict(overall_psi_aggression_factor=1.0, max_psi_retries=25, current_convergence_threshold=1e-6)
+    know = dict(local_solver_preference="direct_solve", is_sparse_problem=False, is_hermitian=False)
+    assert step_population(cands, A, b, strat, know, eng) == C
+    for c in cands:
+        assert c.local_psi_retries_needed == 0 and c.stuck_counter == 0
+        assert np.linalg.norm(A @ c.x_k - b) <= 2e-8 * np.linalg.norm(b)
+        assert abs(c.residual_k - np.linalg.norm(A @ c.x_k - b)) <= 1e-10 * max(1.0, c.residual_k)
