@@ -18,7 +18,8 @@ EXPORTS = [
     "maus_free_pinned", "maus_set_dense", "maus_set_csc", "maus_set_rhs", "maus_upload_vectors",
     "maus_download_vectors", "maus_download_vector_range", "maus_rq", "maus_solve_shifted", "maus_solve_with_R", "maus_mix_residual",
     "maus_residual", "maus_step", "maus_launch_count", "maus_profile_reset", "maus_profile_read", "maus_profile_read_kind", "maus_stream", "maus_debug_zgemm", "maus_svd_set_matrix", "maus_svd_step", "maus_svd_residual",
-    "maus_gram", "maus_project", "maus_nccl_unique_id", "maus_dist_init", "maus_set_csr_rowblock", "maus_rs_matvec", "maus_rs_gmres",
+    "maus_gram", "maus_project", "maus_nccl_unique_id", "maus_dist_init", "maus_dist_info", "maus_gather", "maus_set_csr_rowblock",
+    "maus_rs_set_rhs", "maus_rs_matvec", "maus_rs_gmres", "maus_rs_step",
 ]
 
 
@@ -89,6 +90,10 @@ def load_library():
         "maus_nccl_unique_id": (i32, [C.c_char_p, C.c_char_p]),
         "maus_dist_init": (i32, [vp, C.c_char_p, i32, i32, C.c_char_p]),
         "maus_set_csr_rowblock": (i32, [vp, i64, i64, i64, i64p, i64p, dp]),
+        "maus_dist_info": (i32, [vp, i32p, i32p, i32p]),
+        "maus_gather": (i32, [vp, dp, i64, dp]),
+        "maus_rs_set_rhs": (i32, [vp, dp]),
+        "maus_rs_step": (i32, [vp, i64, i32, i32, dp, dp, dp, u8p, dp, dp, dp, dp, i32p, i32p]),
         "maus_rs_matvec": (i32, [vp, i64, dp, dp]),
         "maus_rs_gmres": (i32, [vp, i64, dp, dp, u8p, dp, dp, i32p, i32p]),
     }

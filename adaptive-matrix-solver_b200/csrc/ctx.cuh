@@ -17,7 +17,8 @@ struct MatrixSlot {
     int* colidx = nullptr;       // nnz
     cplx* vals = nullptr;        // nnz
     cplx* diag = nullptr;        // n, diagonal of the matrix (Jacobi preconditioner, AMS:67)
-    cplx* pack = nullptr;        // [n][4] interleaved copy of up to 4 candidate vectors for the SpMM gathers (spmv.cu)
+    cplx* pack = nullptr;        // groups of [n][4] interleaved candidate vectors for the SpMM gathers (spmv.cu)
+    size_t pack_elems = 0;
     double amax = 0.0;           // max |a_ij| (cabs1), used to gate the sub-ulp Psi perturbation in matvec-only paths
 };
 

@@ -58,7 +58,6 @@ struct GmresWs {
     GmresCand* cand = nullptr;
     int* counters = nullptr;      // [0] = inner_active count, [1] = active count
     int* jacbad = nullptr;        // [C]
-    cplx* red = nullptr;          // [C] compact reduction record (row-sharded mode)
     int* active_idx = nullptr;    // [C] indices of the candidates still iterating (matvec compaction)
     cplx *vc = nullptr, *zc = nullptr;   // [C][n] compacted matvec input / output (allocated when first needed)
     size_t bytes = 0;
@@ -83,19 +82,6 @@ __device__ __forceinline__ void chunk_range(long long n, int nblk, int blk, long
     long long per = (n + nblk - 1) / nblk;
     i0 = (long long)blk * per;
     i1 = i0 + per < n ? i0 + per : n;
-}
-
-// row-sharded mode: every rank holds a slice of each vector, so a partial-sum record must be summed over the ranks before
-// it is consumed.  collapse -> red[b] (compact, all-reduced by NCCL) -> expand back into slot 0 of the record.
-__global__ void gm_collapse_kernel(const cplx* __restrict__ partial, cplx* __restrict__ red, int C, int nblk) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < C) red[b] = sum_partials(partial, b, nblk);
-}
-__global__ void gm_expand_kernel(cplx* __restrict__ partial, const cplx* __restrict__ red, int C, int nblk) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= C) return;
-    partial[b * GM_MAXBLK] = red[b];
-    for (int q = 1; q < nblk; ++q) partial[b * GM_MAXBLK + q] = cmake(0.0, 0.0);
 }
 
 // ---- matvec compaction ---------------------------------------------------------------------------------------------------
@@ -500,7 +486,7 @@ void maus_gmres_free(maus_ctx* ctx) {
     GmresWs* ws = (GmresWs*)ctx->gmres;
     if (!ws) return;
     cudaFree(ws->Vk); cudaFree(ws->w); cudaFree(ws->z); cudaFree(ws->x); cudaFree(ws->r); cudaFree(ws->minv);
-    cudaFree(ws->partial); cudaFree(ws->cand); cudaFree(ws->counters); cudaFree(ws->jacbad); cudaFree(ws->red); cudaFree(ws->active_idx); cudaFree(ws->vc); cudaFree(ws->zc);
+    cudaFree(ws->partial); cudaFree(ws->cand); cudaFree(ws->counters); cudaFree(ws->jacbad); cudaFree(ws->active_idx); cudaFree(ws->vc); cudaFree(ws->zc);
     ctx->bytes_held -= (long long)ws->bytes;
     delete ws;
     ctx->gmres = nullptr;
@@ -524,7 +510,6 @@ static int gmres_ensure(maus_ctx* ctx, long long n, long long C, GmresWs** out) 
     GM_ALLOC(ws->cand, (size_t)ws->C * sizeof(GmresCand));
     GM_ALLOC(ws->counters, 2 * sizeof(int));
     GM_ALLOC(ws->jacbad, (size_t)ws->C * sizeof(int));
-    GM_ALLOC(ws->red, (size_t)ws->C * sizeof(cplx));
     GM_ALLOC(ws->active_idx, (size_t)ws->C * sizeof(int));
     // compaction buffers are part of the workspace: allocating them lazily could fail on ONE rank of a row-sharded solve
     // and make the ranks issue different numbers of collectives
@@ -538,7 +523,7 @@ static int gmres_ensure(maus_ctx* ctx, long long n, long long C, GmresWs** out) 
 }
 
 // The solver proper, written against GmresOperator (gmres.cuh): `n` is the LOCAL vector length, op.matvec applies the
-// shared matrix to C vectors, op.reduce_sync / op.flag_sync make partial sums / flags global in row-sharded mode.
+// shared matrix to C vectors, op.reduce_partials / op.flag_sync make partial sums / flags global in row-sharded mode.
 int gmres_core(maus_ctx* ctx, const GmresOperator& op, long long C, const cplx* sigma, const double* psi,
                const unsigned long long* keys, const unsigned char* use_jacobi, const cplx* rhs, long long rhs_stride, cplx* X,
                int* status, int* iters, double max_psi_host) {
@@ -555,14 +540,11 @@ int gmres_core(maus_ctx* ctx, const GmresOperator& op, long long C, const cplx* 
     const double gate = 1e-17 * std::max(op.amax, 1e-300);
     const bool any_perturb = op.dense && keys && (0.15 * max_psi_host > gate);
     int host_counters[2];
+    // row-sharded mode: every rank holds a slice of each vector, so the per-block partial sums are combined over the ranks
+    // (one kernel over NVLink peer memory, rowshard.cu) before the scalar kernels consume them
     auto sync_partials = [&]() -> int {
-        if (!op.reduce_sync) return MAUS_OK;
-        gm_collapse_kernel<<<gridc, 128, 0, st>>>(ws->partial, ws->red, (int)C, nblk);
-        int r2 = op.reduce_sync(ws->red, C);
-        if (r2) return r2;
-        gm_expand_kernel<<<gridc, 128, 0, st>>>(ws->partial, ws->red, (int)C, nblk);
-        ctx->launches += 2;
-        return MAUS_OK;
+        if (!op.reduce_partials) return MAUS_OK;
+        return op.reduce_partials(ws->partial, GM_MAXBLK, nblk, C);
     };
 #define GM_SYNC() do { if ((rc = sync_partials())) return rc; } while (0)
 

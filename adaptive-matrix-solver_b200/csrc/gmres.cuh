@@ -14,8 +14,9 @@ struct GmresOperator {
     bool dense = false;
     // z[c] (ldz apart) = A * v[c] (ldv apart) for C vectors; v / z are LOCAL slices in row-sharded mode
     std::function<int(const cplx* v, long long ldv, cplx* z, long long ldz, long long C)> matvec;
-    // row-sharded mode only: sum a compact device record of C complex numbers over the ranks, in place
-    std::function<int(cplx* red, long long C)> reduce_sync;
+    // row-sharded mode only: partial [C][maxblk] complex holds nblk per-block partial sums per candidate; replace block 0 by the
+    // sum over blocks AND ranks (same value, same rounding on every rank), zero the other blocks
+    std::function<int(cplx* partial, int maxblk, int nblk, long long C)> reduce_partials;
     // row-sharded mode only: max-combine C device ints over the ranks, in place
     std::function<int(int* flags, long long C)> flag_sync;
 };

@@ -151,7 +151,7 @@ static void free_slot(maus_ctx* ctx, MatrixSlot& s, long long n) {
     maus_dev_free(ctx, s.rm, n * n * sizeof(cplx)); maus_dev_free(ctx, s.cm, n * n * sizeof(cplx));
     maus_dev_free(ctx, s.rowptr, (n + 1) * 8); maus_dev_free(ctx, s.colidx, s.nnz * 4);
     maus_dev_free(ctx, s.vals, s.nnz * sizeof(cplx)); maus_dev_free(ctx, s.diag, n * sizeof(cplx));
-    if (s.pack) maus_dev_free(ctx, s.pack, n * 4 * sizeof(cplx));
+    if (s.pack) maus_dev_free(ctx, s.pack, s.pack_elems * sizeof(cplx));
     s = MatrixSlot();
 }
 
@@ -438,10 +438,16 @@ int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cpl
     }
     if (s.sparse) {
         int h = prof_begin(ctx, MAUS_PROF_MATVEC, (double)((C + 3) / 4) * (20.0 * s.nnz + 8.0 * (n + 1)) + 32.0 * n * C);
-        if (C > 1 && !s.pack) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.pack, (size_t)n * 4 * sizeof(cplx)));
+        const size_t need = csr_spmm_pack_elems(n, (int)C);
+        if (need > s.pack_elems) {
+            MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            maus_dev_free(ctx, s.pack, s.pack_elems * sizeof(cplx)); s.pack = nullptr; s.pack_elems = 0;
+            MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.pack, need * sizeof(cplx)));
+            s.pack_elems = need;
+        }
         MAUS_CUDA(ctx, csr_spmm(s.rowptr, s.colidx, s.vals, V, ldv, Y, ldy, n, n, (int)C, C > 1 ? s.pack : nullptr, ctx->stream));
         prof_end(ctx, h);
-        ctx->launches += (C + 3) / 4 + (C > 1 ? (C + 3) / 4 - (C % 4 == 1 ? 1 : 0) : 0);   // SpMM passes + pack passes
+        ctx->launches += (C > 1) ? 2 : 1;          // interleave pass + one SpMM launch over all groups of 4
         return MAUS_OK;
     }
     return maus_fail(ctx, MAUS_E_STATE, "matrix slot not set");

@@ -532,6 +532,39 @@ cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int 
     return cudaGetLastError();
 }
 
+// ---- explicit halves of the multi-block reductions (row-sharded vectors, rowshard.cu): every rank runs the `part` kernel on
+// its slice, the per-block partials in `scratch` are combined over the ranks, then the `final` / `apply` kernel runs ----
+int vec_part_blocks(long long n) { return vmb_blocks((int)n); }
+cudaError_t vec_rq_part(const cplx* V, const cplx* Y, int n, int C, double* scratch, int nblk, cudaStream_t stream) {
+    rq_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, scratch);
+    return cudaGetLastError();
+}
+cudaError_t vec_rq_final(const double* scratch, int nblk, int C, cplx* lambda, double* vnorm2, int* status, cudaStream_t stream) {
+    rq_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(scratch, nblk, C, lambda, vnorm2, status);
+    return cudaGetLastError();
+}
+cudaError_t vec_mix_part(cplx* V, const cplx* X, int n, int C, const double* alpha, const int* status, double* scratch, int nblk,
+                         cudaStream_t stream) {
+    mix_preset_kernel<<<(C + 127) / 128, 128, 0, stream>>>(status, C, scratch);
+    mix_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, X, n, alpha, status, scratch);
+    return cudaGetLastError();
+}
+cudaError_t vec_mix_apply(cplx* V, int n, int C, int problem_type, double* mixnorm, int* status, const double* scratch, int nblk,
+                          cudaStream_t stream) {
+    mix_apply_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, n, problem_type, mixnorm, status, scratch);
+    return cudaGetLastError();
+}
+cudaError_t vec_res_part(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda, const cplx* b,
+                         double* scratch, int nblk, cudaStream_t stream) {
+    res_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch);
+    return cudaGetLastError();
+}
+cudaError_t vec_res_final(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda, const cplx* b,
+                          const double* scratch, int nblk, double* resid, cudaStream_t stream) {
+    res_final_kernel<<<C, RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch, nblk, resid);
+    return cudaGetLastError();
+}
+
 template <int RPW, int GV_NT>
 static void gemv_launch(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int nrows, int n, int C,
                         cudaStream_t stream) {

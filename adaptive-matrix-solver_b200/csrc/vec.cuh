@@ -37,3 +37,20 @@ cudaError_t vec_gemv_rect(const cplx* A_rm, int nrows, int ncols, const cplx* V,
 
 // G[i][j] = <v_i, v_j> = sum_k conj(v_i[k]) v_j[k] for C vectors of length n ([C][n]); G is [C][C] row-major
 cudaError_t vec_gram(const cplx* V, int n, int C, cplx* G, cudaStream_t stream);
+
+// explicit halves of the multi-block reductions for row-sharded vectors (rowshard.cu).  scratch: [C][VEC_PART_MAXBLK][4] doubles;
+// a `part` kernel fills blocks 0 .. nblk-1 of every candidate, the caller combines them over the ranks (component-wise sum or
+// max, see rowshard.cu) and the `final` / `apply` kernel reads them back.  The rare scaled-norm recomputation of the final
+// kernels (plain sum of squares out of range) only sees the local slice: not supported for sharded vectors.
+constexpr int VEC_PART_MAXBLK = 64;
+int vec_part_blocks(long long n);
+cudaError_t vec_rq_part(const cplx* V, const cplx* Y, int n, int C, double* scratch, int nblk, cudaStream_t stream);          // comps 0,1,2: sums
+cudaError_t vec_rq_final(const double* scratch, int nblk, int C, cplx* lambda, double* vnorm2, int* status, cudaStream_t stream);
+cudaError_t vec_mix_part(cplx* V, const cplx* X, int n, int C, const double* alpha, const int* status, double* scratch, int nblk,
+                         cudaStream_t stream);                                                                                 // comp 0: max (-1 = skipped), 1: sum
+cudaError_t vec_mix_apply(cplx* V, int n, int C, int problem_type, double* mixnorm, int* status, const double* scratch, int nblk,
+                          cudaStream_t stream);
+cudaError_t vec_res_part(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda, const cplx* b,
+                         double* scratch, int nblk, cudaStream_t stream);                                                      // comp 0: max, 1: sum, 3: max
+cudaError_t vec_res_final(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda, const cplx* b,
+                          const double* scratch, int nblk, double* resid, cudaStream_t stream);

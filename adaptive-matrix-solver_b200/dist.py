@@ -20,8 +20,10 @@ NREC = len(REC_FIELDS)
 
 
 class Shard:
-    def __init__(self, rank=0, world=1, device=None):
-        self.rank, self.world, self.device = int(rank), int(world), device
+    def __init__(self, rank=0, world=1, device=None, engine=None):
+        """``engine``: a MausEngine set up with ``enable_row_sharding`` -- the per-generation exchange then runs through the
+        library's own ``maus_gather`` (NCCL all-gather on the context's stream) instead of torch.distributed."""
+        self.rank, self.world, self.device, self.engine = int(rank), int(world), device, engine
 
     def owned(self, live_count):
         """indices (into the live list) this rank steps: round-robin, re-balanced every generation"""
@@ -38,10 +40,14 @@ class Shard:
         import torch
         if self.world == 1:
             return [local]
-        dist = self._dist()
         cols = local.shape[1]
         buf = np.zeros((max_rows, cols), dtype=np.float64)
         buf[:local.shape[0]] = local
+        rs = getattr(self.engine, "rowshard", None) if self.engine is not None else None
+        if rs is not None and rs.world == self.world:
+            out = rs.gather(buf).reshape(self.world, max_rows, cols)
+            return [out[r] for r in range(self.world)]
+        dist = self._dist()
         t = torch.from_numpy(buf)
         if self.device is not None:
             t = t.to(self.device, non_blocking=False)
@@ -127,6 +133,10 @@ def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, e
     if live[0].problem_type.value not in (_abi.EIGENVALUE, _abi.SOLVE_LINEAR_SYSTEM):
         # SVD / other branches: not sharded (every rank steps its own replica of the whole population)
         return step_population(candidates, M, b, strat_params, problem_knowledge, engine)
+    if _uses_row_sharding(live, M, problem_knowledge, engine):
+        # the MATRIX is sharded, not the population: every rank passes all live candidates to the collective row-sharded step
+        # and receives the full updated vectors; statuses (and with them the host RNG draws) are identical on every rank
+        return step_population(candidates, M, b, strat_params, problem_knowledge, engine)
     n = live[0].N_diag
     eigen = live[0].problem_type.value == _abi.EIGENVALUE
     counts = [len(range(r, len(live), shard.world)) for r in range(shard.world)]
@@ -171,6 +181,17 @@ def _resync_host_rng(gathered, counts):
     np.random.seed(seed % (2 ** 32))
     random.seed(seed)
     return True
+
+
+def _uses_row_sharding(live, M, problem_knowledge, engine):
+    """mirror of the routing test in population.step_population"""
+    from .constants import LU_MAX_N
+    from .population import _is_sparse
+    rs = getattr(engine, "rowshard", None)
+    pref = problem_knowledge.get('local_solver_preference', 'direct_solve')
+    hermitian_eigen = live[0].problem_type.value == _abi.EIGENVALUE and bool(problem_knowledge.get('is_hermitian', False))
+    return (rs is not None and not hermitian_eigen and _is_sparse(M) and (pref == 'iterative_gmres' or live[0].N_diag > LU_MAX_N)
+            and all(c.problem_matrix is M for c in live))
 
 
 def gather_energy_and_best(shard, resid, lam, vectors, best_index=None):

@@ -41,6 +41,7 @@ class MausEngine:
         self.is_sparse = False
         self.generation = 0
         self.matrix_epoch = [0, 0]          # uploads per slot; population._MatrixCache compares it (shared-engine safety)
+        self.rowshard = None                # RowShardedOperator of this context (rowshard.py), set by enable_row_sharding
         self._pinned = []
         if workspace_limit_bytes:
             self._check(self._lib.maus_set_workspace_limit(self._h, int(workspace_limit_bytes)))
@@ -64,6 +65,15 @@ class MausEngine:
             self.close()
         except Exception:
             pass
+
+    def enable_row_sharding(self, rank, world, broadcast=None):
+        """Multi-GPU set-up of the context (one process per GPU): NCCL communicator + the row-sharded sparse operator.  After
+        this call ``step_population`` runs sparse GMRES problems with the matrix row-sharded over the ranks (BASELINE config 5
+        as worded) and ``dist.Shard`` can use ``maus_gather`` for the per-generation exchange."""
+        from .rowshard import RowShardedOperator
+        if self.rowshard is None or self.rowshard.world != int(world) or self.rowshard.rank != int(rank):
+            self.rowshard = RowShardedOperator(self, rank, world, broadcast)
+        return self.rowshard
 
     def pinned_empty(self, shape, dtype=_c128):
         """numpy array backed by page-locked host memory (for the e2e path)."""

@@ -99,6 +99,31 @@ def _ladder(engine, ptype, v_or_x, lam, stuck, base_psi, max_attempts, pref, mat
     return None, attempts
 
 
+def _ladder_rs(rs, ptype, v_or_x, lam, stuck, alpha, base_psi, max_attempts, pref):
+    """``_ladder`` on the row-sharded operator (every rank walks it identically: the status words are global).  A GMRES attempt
+    is ONE collective call that also mixes and takes the residual (phases solve | mix | residual); a direct-solve attempt has no
+    device counterpart for a row-sharded sparse matrix and counts as failed (AMS:57 is SuperLU, out of scope).
+    Returns (vector or None, residual, status, num_psi_attempts)."""
+    fallback = 'iterative_gmres' if pref == 'direct_solve' else 'direct_solve'
+    method, attempts, pending_failure = pref, 0, True
+    while attempts < max_attempts:
+        if not pending_failure and _METHOD.get(method) == _abi.METHOD_GMRES:
+            psi = psi_magnitude(base_psi, attempts, stuck)
+            V1 = np.ascontiguousarray(v_or_x[None, :], dtype=np.complex128).copy()
+            out = rs.step(ptype, V1, [alpha], [complex(psi).real], use_jacobi=[1 if stuck > 1 else 0],
+                          sigma=[lam] if ptype == _abi.EIGENVALUE else None, phases=14)
+            st = int(out["status"][0])
+            if st in (_abi.ST_OK, _abi.ST_MIX_COLLAPSED):
+                return V1[0], float(out["resid"][0]), st, attempts
+        pending_failure = False
+        if method == pref and pref != fallback and attempts == 0:          # AMS:99-102
+            method = fallback
+            attempts = 0
+            continue
+        attempts += 1                                                      # AMS:103
+    return None, np.inf, _abi.ST_GMRES_NOCONV, attempts
+
+
 def step_population(candidates, M, b, strat_params, problem_knowledge, engine, cache=None):
     """Batched equivalent of the loop AMS:574-576.  Returns the number of candidates stepped on the GPU."""
     if not candidates:
@@ -141,6 +166,21 @@ def step_population(candidates, M, b, strat_params, problem_knowledge, engine, c
     # matrix residency.  Direct solves need the dense form; a sparse problem that prefers the direct solver
     # (reference: SuperLU, AMS:57) is densified when it fits the batched LU, otherwise that try fails -> GMRES.
     m_sparse = _is_sparse(M)
+    # Row-sharded operator (BASELINE config 5 as worded): when the context was set up with ``enable_row_sharding`` a sparse
+    # problem on the GMRES path keeps only n / G rows of the matrix per GPU; every rank steps ALL candidates jointly.
+    rs = getattr(engine, "rowshard", None)
+    if not (rs is not None and m_sparse and (pref == 'iterative_gmres' or N > LU_MAX_N)
+            and all(c.problem_matrix is M for c in gpu)):
+        rs = None
+    if rs is not None:
+        rs.ensure_matrix(M)
+        if ptype == _abi.SOLVE_LINEAR_SYSTEM:
+            rs.set_rhs(b)
+        for c in gpu:
+            c.b_vector = b                                                                     # AMS:146
+            c.prev_residual = c.residual_k                                                     # AMS:147
+        _step_group(gpu, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, _abi.SLOT_CURRENT, rs)
+        return len(gpu)
     if pref == 'direct_solve' and m_sparse and N <= LU_MAX_N:
         form = 'dense'
     else:
@@ -168,7 +208,7 @@ def step_population(candidates, M, b, strat_params, problem_knowledge, engine, c
     return len(gpu)
 
 
-def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, res_slot):
+def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, res_slot, rs=None):
     C_ = len(cands)
     eigen = ptype == _abi.EIGENVALUE
     # the vectors travel through one page-locked staging buffer (H2D before, D2H after the fused step)
@@ -191,9 +231,14 @@ def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, 
     gen = engine.generation
     keys = None if is_sparse else np.array([_key(c.id, gen, 0) for c in cands], dtype=np.uint64)
     method0 = _METHOD.get(pref)
-    if method0 is None or (method0 == _abi.METHOD_LU and (engine.is_sparse or N > LU_MAX_N)):
+    if rs is not None and method0 == _abi.METHOD_GMRES:
+        out = rs.step(ptype, V, alpha, psi0, use_jacobi=(stuck > 1).astype(np.uint8), phases=15)
+    elif method0 is None or (method0 == _abi.METHOD_LU and (rs is not None or engine.is_sparse or N > LU_MAX_N)):
         # unknown method / direct solve beyond the LU limit (sparse or dense): the first try fails for everybody (AMS:92, 98)
-        out = dict(lam=engine.rq(V)[0] if eigen else np.zeros(C_, dtype=np.complex128),
+        lam0 = np.zeros(C_, dtype=np.complex128)
+        if eigen:
+            lam0 = rs.step(ptype, V, phases=1)["lam"] if rs is not None else engine.rq(V)[0]
+        out = dict(lam=lam0,
                    resid=np.full(C_, np.inf), mixnorm=np.zeros(C_), status=np.full(C_, _abi.ST_ZERO_PIVOT, dtype=np.int32),
                    iters=np.zeros(C_, dtype=np.int32))
     else:
@@ -208,7 +253,15 @@ def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, 
         if eigen:
             c.lambda_k = np.complex128(lam[i])                                                  # AMS:268 (0 when |<v,v>| tiny)
         need_residual = False
-        if st in (_abi.ST_ZERO_PIVOT, _abi.ST_NONFINITE, _abi.ST_GMRES_NOCONV):
+        if st in (_abi.ST_ZERO_PIVOT, _abi.ST_NONFINITE, _abi.ST_GMRES_NOCONV) and rs is not None:
+            vec, r1, st1, retries = _ladder_rs(rs, ptype, V_before[i], complex(lam[i]), int(stuck[i]), float(alpha[i]), base_psi,
+                                               max_retries, pref)
+            if vec is not None:
+                V[i] = vec
+                resid[i] = r1
+                st = st1
+                solved = True
+        elif st in (_abi.ST_ZERO_PIVOT, _abi.ST_NONFINITE, _abi.ST_GMRES_NOCONV):
             # the preferred method failed at attempt 0: walk the rest of the ladder for this candidate
             x, retries = _ladder(engine, ptype, V_before[i], complex(lam[i]), int(stuck[i]), base_psi, max_retries,
                                  pref, is_sparse, c.id)
@@ -243,7 +296,11 @@ def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, 
             need_residual = True
         if need_residual:                                                                       # AMS:295-299
             vec = c.v_k if eigen else c.x_k
-            resid[i] = engine.residual(ptype, vec[None, :], [c.lambda_k] if eigen else None, res_slot=res_slot)[0]
+            if rs is not None:
+                V1 = np.ascontiguousarray(vec[None, :], dtype=np.complex128).copy()
+                resid[i] = rs.step(ptype, V1, sigma=[c.lambda_k] if eigen else None, phases=8)["resid"][0]
+            else:
+                resid[i] = engine.residual(ptype, vec[None, :], [c.lambda_k] if eigen else None, res_slot=res_slot)[0]
         c.residual_k = np.float64(resid[i])
         c.param_history.append(c.get_current_solution_params())                                # AMS:303-304
         c.residual_history.append(c.residual_k)

@@ -88,6 +88,57 @@ class RowShardedOperator:
                 ident = broadcast(ident)
         engine._check(self._lib.maus_dist_init(engine._h, lib, self.rank, self.world, ident))
         self.n = self.row0 = self.nloc = 0
+        self._matrix = None
+
+    def info(self):
+        r, w, p = C.c_int32(), C.c_int32(), C.c_int32()
+        self.engine._check(self._lib.maus_dist_info(self.engine._h, C.byref(r), C.byref(w), C.byref(p)))
+        return dict(rank=r.value, world=w.value, peer_memory=bool(p.value))
+
+    def mode_description(self):
+        pm = self.info()["peer_memory"]
+        return (f"matrix row-sharded x{self.world}; " +
+                ("NVLink peer memory: pack + all-gather fused into one store kernel, one-kernel rank-ordered reductions"
+                 if pm else "NCCL transport: all-gather per SpMM, all-reduce per dot product"))
+
+    def ensure_matrix(self, A):
+        """upload this rank's row block of A unless the same object is already resident"""
+        if self._matrix is not A:
+            self.set_matrix(A)
+            self._matrix = A
+
+    def gather(self, send):
+        """all-gather a float64 array of identical length from every rank (NCCL all-gather on the context's stream,
+        ``maus_gather``); returns [world][len]"""
+        send = np.ascontiguousarray(send, dtype=np.float64).ravel()
+        out = np.empty((self.world, send.size), dtype=np.float64)
+        self.engine._check(self._lib.maus_gather(self.engine._h, _dp(send), send.size, _dp(out)))
+        return out
+
+    def set_rhs(self, b):
+        b = np.ascontiguousarray(b, dtype=_c128)
+        if b.shape != (self.n,):
+            raise ValueError("b must be the full right-hand side [n]")
+        self.engine._check(self._lib.maus_rs_set_rhs(self.engine._h, _dp(b)))
+
+    PH_RQ, PH_SOLVE, PH_MIX, PH_RESIDUAL = 1, 2, 4, 8
+
+    def step(self, problem_type, V, alpha=None, psi=None, use_jacobi=None, sigma=None, phases=15):
+        """``maus_rs_step``: one generation (phases 15), one ladder attempt (14 with sigma) or a residual (8 with sigma) for C
+        candidates that every rank passes identically; V [C][n] full-length, updated in place on every rank."""
+        if V.dtype != _c128 or not V.flags.c_contiguous or V.ndim != 2 or V.shape[1] != self.n:
+            raise ValueError("V must be a C-contiguous complex128 [C][n] array (updated in place)")
+        C_ = V.shape[0]
+        f64 = lambda a: None if a is None else np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)      # noqa: E731
+        alpha, psi = f64(alpha), f64(psi)
+        jac = None if use_jacobi is None else np.ascontiguousarray(np.atleast_1d(use_jacobi), dtype=np.uint8)
+        sig = None if sigma is None else np.ascontiguousarray(np.atleast_1d(sigma), dtype=_c128)
+        out = dict(lam=np.empty(C_, dtype=_c128), resid=np.empty(C_, dtype=np.float64), mixnorm=np.empty(C_, dtype=np.float64),
+                   status=np.empty(C_, dtype=np.int32), iters=np.empty(C_, dtype=np.int32))
+        self.engine._check(self._lib.maus_rs_step(
+            self.engine._h, C_, int(problem_type), int(phases), _dp(V), _dp(alpha), _dp(psi), _ip(jac, C.c_uint8), _dp(sig),
+            _dp(out["lam"]), _dp(out["resid"]), _dp(out["mixnorm"]), _ip(out["status"], C.c_int32), _ip(out["iters"], C.c_int32)))
+        return out
 
     def set_matrix(self, A):
         """A: the FULL scipy.sparse matrix (every rank slices its own rows) -- or use ``set_row_block`` directly"""
@@ -100,6 +151,7 @@ class RowShardedOperator:
         self.engine._check(self._lib.maus_set_csr_rowblock(self.engine._h, int(n), int(row0), int(nloc),
                                                            _ip(rowptr, C.c_int64), _ip(colidx, C.c_int64), _dp(vals)))
         self.n, self.row0, self.nloc = int(n), int(row0), int(nloc)
+        self._matrix = None
 
     def local(self, full):
         """slice [..., row0:row0+nloc] of full-length vector(s)"""

@@ -13,8 +13,8 @@
  *     maus_last_error() returns the text of the last failure of that context.
  *   - complex128 = two consecutive doubles (re, im), exactly numpy's layout.  All host buffers are caller-owned,
  *     C-contiguous; "V[C][n]" means candidate c's vector is the n complex numbers starting at V + 2*n*c.
- *   - one context = one GPU = one host thread (one process per GPU; multi-GPU is candidate sharding done by
- *     the host layer with torch.distributed / NCCL, see adaptive-matrix-solver_b200/dist.py).
+ *   - one context = one GPU = one host thread (one process per GPU; multi-GPU = candidate sharding with one all-gather per
+ *     generation (maus_gather; host logic in adaptive-matrix-solver_b200/dist.py) or the row-sharded operator (maus_rs_*)).
  *   - there is NO CPU fallback: without a CUDA device maus_create fails with MAUS_E_CUDA.
  */
 #ifndef MAUS_B200_H
@@ -165,22 +165,44 @@ int maus_gram(maus_ctx* ctx, int64_t C, int64_t n, const double* V, double* G_ou
  * ([n][m] complex128), V [C][n], P_out [C][m]. */
 int maus_project(maus_ctx* ctx, int64_t n, int64_t m, const double* Ec, int64_t C, const double* V, double* P_out);
 
-/* ---- row-sharded sparse operator (BASELINE config 5 as worded) ---------------------------------- */
-/* Every rank owns n / world consecutive rows of A and the same slice of every vector; a matvec all-gathers its input,
- * GMRES all-reduces its dot products (NCCL over NVLink, bound at run time from `libpath` = the libnccl.so.2 the process
- * already uses, e.g. torch's).  rank 0 creates the id, the host layer broadcasts the 128 bytes. */
+/* ---- multi-GPU: NCCL communicator of the context + row-sharded sparse operator (BASELINE config 5) -------- */
+/* One process per GPU.  rank 0 creates the id, the host layer broadcasts the 128 bytes (torch.distributed or anything else);
+ * NCCL is bound at run time from `libpath` = the libnccl.so.2 the process already uses (e.g. torch's), so libmaus_b200.so has
+ * no link-time dependency on it. */
 int maus_nccl_unique_id(const char* libpath, char* out128);
 int maus_dist_init(maus_ctx* ctx, const char* libpath, int rank, int world, const char* id128);
-/* CSR slice of rows [row0, row0 + nrows): rowptr has nrows + 1 entries (any base), colidx are GLOBAL column indices;
- * rowptr / colidx / vals point at the START of the full arrays' slice, i.e. rowptr[i] indexes colidx / vals directly */
+/* rank / world of the context; peer_memory = 1 when the row-sharded operator runs on NVLink peer memory (cudaIpc-mapped
+ * symmetric segments: fused pack + all-gather stores, one-kernel reductions), 0 when it fell back to NCCL calls */
+int maus_dist_info(maus_ctx* ctx, int* rank, int* world, int* peer_memory);
+/* candidate-sharded mode: the per-generation all-gather of SURVEY.md 8e (candidate records + vectors, or energies + the best
+ * eigenpair): `count` doubles from every rank, recv_all [world][count]; NCCL all-gather on the context's stream. */
+int maus_gather(maus_ctx* ctx, const double* send, int64_t count, double* recv_all);
+
+/* Row-sharded operator: every rank owns n / world consecutive rows of A (CSR slice, GLOBAL column indices) and the same slice
+ * of every vector.  rowptr has nrows + 1 entries (any base); rowptr / colidx / vals point at the START of the full arrays'
+ * slice, i.e. rowptr[i] indexes colidx / vals directly. */
 int maus_set_csr_rowblock(maus_ctx* ctx, int64_t n, int64_t row0, int64_t nrows, const int64_t* rowptr,
                           const int64_t* colidx, const double* vals);
+/* right-hand side of SOLVE_LINEAR_SYSTEM for the row-sharded operator (full vector; the rank keeps its slice) */
+int maus_rs_set_rhs(maus_ctx* ctx, const double* b_full);
 /* Y_local[c] = (A V[c])(local rows); V_local, Y_local: [C][nrows] */
 int maus_rs_matvec(maus_ctx* ctx, int64_t C, const double* V_local, double* Y_local);
 /* x_c = (A - sigma_c I + psi_c I)^-1 rhs_c with the batched GMRES of maus_solve_shifted on the row-sharded operator;
  * RHS_local / X_local_out are the local slices [C][nrows]; status / iters are identical on every rank */
 int maus_rs_gmres(maus_ctx* ctx, int64_t C, const double* sigma, const double* psi, const uint8_t* use_jacobi,
                   const double* RHS_local, double* X_local_out, int32_t* status_out, int32_t* iters_out);
+/* maus_step on the row-sharded operator (Seam B for config 5 as worded): every rank passes the SAME C candidates; V_full_io
+ * [C][n] full-length host vectors (v_k / x_k), updated in place on every rank.  phases: 1 Rayleigh quotient (AMS:264-270) |
+ * 2 solve (AMS:44-97, GMRES; sparse: R = 0) | 4 mix + normalise (AMS:280-285) | 8 residual (AMS:295-299); 15 = one generation,
+ * 14 with sigma_in = one attempt of the retry ladder (AMS:98-103) for a candidate whose first try failed, 8 = residual only
+ * (after the host replaced a vector).  Without phase 1, sigma_in [C] complex supplies the shifts = stale lambdas (eigen). */
+#define MAUS_RS_PHASE_RQ       1
+#define MAUS_RS_PHASE_SOLVE    2
+#define MAUS_RS_PHASE_MIX      4
+#define MAUS_RS_PHASE_RESIDUAL 8
+int maus_rs_step(maus_ctx* ctx, int64_t C, int problem_type, int phases, double* V_full_io, const double* alpha,
+                 const double* psi, const uint8_t* use_jacobi, const double* sigma_in, double* lambda_out, double* resid_out,
+                 double* mixnorm_out, int32_t* status_out, int32_t* iters_out);
 
 /* debug / parity: C = beta*C + s*A*B on column-major complex128 host matrices (A: M x K, B: K x N, C: M x N,
  * `batch` of each, densely packed) through the tensor-pipe kernel (use_dmma = 1; 2 = the three-real-product
