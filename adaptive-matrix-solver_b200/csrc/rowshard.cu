@@ -57,7 +57,7 @@ constexpr int RS_MAXG = 16;            // ranks of one NVSwitch domain
 constexpr int RS_RED_SLOTS = 4;        // a rank is at most one reduction ahead of the slowest peer; 4 slots leave margin
 constexpr int RS_RED_COMP = 4;         // doubles per candidate and reduction
 constexpr int RS_PUSH_ROWS = 64;       // rows per CTA of the push kernel: 64 x 4 x 16 B = one 4 KB piece per destination
-constexpr long long RS_SPIN_LIMIT = 6000000000LL;   // ~3 s of SM clocks: a lost peer sets the error flag instead of hanging the GPU
+constexpr long long RS_SPIN_LIMIT = 40000000000LL;  // ~20 s of SM clocks: a lost peer sets the error flag instead of hanging the GPU
 
 // flag words at the head of the segment (unsigned long long each)
 constexpr int RS_F_XREADY = 0;                          // [2][RS_MAXG]  push of buffer b by rank r complete (sequence number)
