@@ -17,8 +17,11 @@
 #include <algorithm>
 #include <cfloat>
 #include <functional>
+#include <cooperative_groups.h>
 #include "ctx.cuh"
 #include "gmres.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -59,7 +62,9 @@ struct GmresWs {
     int* counters = nullptr;      // [0] = inner_active count, [1] = active count
     int* jacbad = nullptr;        // [C]
     int* active_idx = nullptr;    // [C] indices of the candidates still iterating (matvec compaction)
-    cplx *vc = nullptr, *zc = nullptr;   // [C][n] compacted matvec input / output (allocated when first needed)
+    cplx *vc = nullptr, *zc = nullptr;   // [C][n] compacted matvec input / output
+    int* host_poll = nullptr;            // pinned [2]: inner-active counts read back with a lag of one iteration
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     size_t bytes = 0;
 };
 
@@ -381,14 +386,10 @@ __device__ void zlartg_dev(cplx f, cplx g, double& c, cplx& s, cplx& r) {
     r = cmake(fu.x * d, fu.y * d);
 }
 
-// end of an inner iteration (scipy lines 772-805): h1, breakdown, Givens, presid, loop exit test
-__global__ void gm_hess_kernel(GmresCand* cand, const cplx* partial, int C, int nblk, int m, int* counters) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= C) return;
-    GmresCand& g = cand[b];
-    if (!g.active || !g.inner_active) return;
+// end of an inner iteration (scipy lines 772-805): h1, breakdown, Givens, presid, loop exit test.  The column h[col][0..col] is
+// already in g.h; returns true when the candidate leaves the inner loop after storing v[col + 1] once more.
+__device__ bool gm_hess_update(GmresCand& g, double h1, int m) {
     const int col = g.col;
-    const double h1 = sqrt(sum_partials(partial, b, nblk).x);
     g.h[col][col + 1] = cmake(h1, 0.0);
     if (h1 <= DBL_EPSILON * g.h0) { g.h[col][col + 1] = cmake(0.0, 0.0); g.breakdown = 1; g.scale = 1.0; }
     else g.scale = 1.0 / h1;
@@ -409,9 +410,122 @@ __global__ void gm_hess_kernel(GmresCand* cand, const cplx* partial, int C, int 
     g.presid = hypot(tmp.x, tmp.y);
     g.inner_iter += 1;
     g.last_col = col;
-    if (g.presid <= g.ptol || g.breakdown || col + 1 >= m) g.inner_active = 2;   // 2 = store v[col+1] once more, then leave
+    return g.presid <= g.ptol || g.breakdown || col + 1 >= m;
+}
+__global__ void gm_hess_kernel(GmresCand* cand, const cplx* partial, int C, int nblk, int m, int* counters) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= C) return;
+    GmresCand& g = cand[b];
+    if (!g.active || !g.inner_active) return;
+    const double h1 = sqrt(sum_partials(partial, b, nblk).x);
+    if (gm_hess_update(g, h1, m)) g.inner_active = 2;                      // 2 = store v[col+1] once more, then leave
     else atomicAdd(&counters[0], 1);
 }
+
+// ---- whole inner iteration in ONE launch for vectors that fit a thread-block cluster (n <= 32768: the dense configurations) ----
+// After the batched matvec z = A v[col], a cluster of up to 8 CTAs owns one candidate and keeps its slice of w in REGISTERS:
+//   w = M (z + shift v[col]) ; h0 = |w| ; for k <= col: h[col][k] = <v[k], w>, w -= h[col][k] v[k] ; h1 = |w| ;
+//   Hessenberg / Givens / stopping logic (CTA 0, one thread) ; v[col + 1] = w * scale ; advance.
+// Same arithmetic sequence as the multi-launch path (modified Gram-Schmidt in scipy's order), but every v[k] is read once
+// instead of three vector passes per k, and the 2 (col + 1) + 6 launches of the multi-launch path become one.  Dot products:
+// warp shuffle -> CTA (fixed order) -> distributed shared memory, one cluster barrier per reduction, summed in CTA-rank order
+// by every CTA (deterministic).
+constexpr int GA_NT = 256, GA_MAXC = 8;
+template <int EPT>
+__global__ void __launch_bounds__(GA_NT) gm_arnoldi_cluster_kernel(const cplx* __restrict__ z, cplx* __restrict__ Vk,
+                                                                   const cplx* __restrict__ minv, GmresCand* cand, long long n,
+                                                                   int m, int col, int* counters) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int NC = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / NC;
+    GmresCand& g = cand[b];
+    if (!g.active || !g.inner_active) return;                  // uniform over the cluster: nobody reaches a cluster barrier
+    __shared__ cplx slots[2][GA_MAXC];
+    __shared__ cplx wsum[GA_NT / 32];
+    __shared__ double s_scale;
+    __shared__ int s_leave;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int red = 0;
+    auto cluster_sum = [&](cplx v) -> cplx {
+        v = warp_sum(v);
+        if (lane == 0) wsum[warp] = v;
+        __syncthreads();
+        if (t == 0) {
+            cplx tot = cmake(0.0, 0.0);
+            for (int q = 0; q < GA_NT / 32; ++q) { tot.x += wsum[q].x; tot.y += wsum[q].y; }
+            for (int d = 0; d < NC; ++d) *cluster.map_shared_rank(&slots[red & 1][rank], d) = tot;
+        }
+        cluster.sync();
+        cplx r = cmake(0.0, 0.0);
+        for (int d = 0; d < NC; ++d) { const cplx p = slots[red & 1][d]; r.x += p.x; r.y += p.y; }
+        ++red;
+        return r;
+    };
+    const long long stride = (long long)NC * GA_NT, i0 = (long long)rank * GA_NT + t;
+    const cplx* zb = z + (long long)b * n;
+    const cplx* mb = minv + (long long)b * n;
+    cplx* vb = Vk + (long long)b * (m + 1) * n;
+    const bool jac = g.jac_on;
+    const cplx sft = g.shift;
+    cplx w[EPT];
+    double s = 0.0;
+    {
+        const cplx* v = vb + (long long)col * n;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const long long i = i0 + e * stride;
+            cplx wv = cmake(0.0, 0.0);
+            if (i < n) {
+                cplx av = zb[i];
+                cfma(av, sft, v[i]);
+                wv = jac ? cmul(mb[i], av) : av;
+            }
+            w[e] = wv;
+            s = fma(wv.x, wv.x, s); s = fma(wv.y, wv.y, s);
+        }
+    }
+    const double h0 = sqrt(cluster_sum(cmake(s, 0.0)).x);
+    for (int k = 0; k <= col; ++k) {
+        const cplx* vk = vb + (long long)k * n;
+        cplx vv[EPT];
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const long long i = i0 + e * stride;
+            vv[e] = (i < n) ? vk[i] : cmake(0.0, 0.0);
+            cfma_conj(acc, vv[e], w[e]);                        // vdot(v[k], w) = sum conj(v) * w
+        }
+        const cplx hk = cluster_sum(acc);
+        if (rank == 0 && t == 0) g.h[col][k] = hk;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) cfms(w[e], hk, vv[e]);
+    }
+    double s2 = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) { s2 = fma(w[e].x, w[e].x, s2); s2 = fma(w[e].y, w[e].y, s2); }
+    const double h1 = sqrt(cluster_sum(cmake(s2, 0.0)).x);
+    if (rank == 0 && t == 0) {
+        g.h0 = h0;
+        const bool leave = gm_hess_update(g, h1, m);
+        const double sc = g.scale;
+        for (int d = 0; d < NC; ++d) { *cluster.map_shared_rank(&s_scale, d) = sc; *cluster.map_shared_rank(&s_leave, d) = leave ? 1 : 0; }
+    }
+    cluster.sync();
+    const double sc = s_scale;
+    {
+        cplx* vn = vb + (long long)(col + 1) * n;              // v[col + 1] = w * scale (stored also when leaving: scipy line 806)
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const long long i = i0 + e * stride;
+            if (i < n) vn[i] = cmake(w[e].x * sc, w[e].y * sc);
+        }
+    }
+    if (rank == 0 && t == 0) {
+        if (s_leave) g.inner_active = 0;
+        else { g.col = col + 1; atomicAdd(&counters[0], 1); }
+    }
+}
+
 __global__ void gm_advance_kernel(GmresCand* cand, int C) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= C) return;
@@ -487,6 +601,8 @@ void maus_gmres_free(maus_ctx* ctx) {
     if (!ws) return;
     cudaFree(ws->Vk); cudaFree(ws->w); cudaFree(ws->z); cudaFree(ws->x); cudaFree(ws->r); cudaFree(ws->minv);
     cudaFree(ws->partial); cudaFree(ws->cand); cudaFree(ws->counters); cudaFree(ws->jacbad); cudaFree(ws->active_idx); cudaFree(ws->vc); cudaFree(ws->zc);
+    if (ws->host_poll) cudaFreeHost(ws->host_poll);
+    for (auto& e : ws->poll_ev) if (e) cudaEventDestroy(e);
     ctx->bytes_held -= (long long)ws->bytes;
     delete ws;
     ctx->gmres = nullptr;
@@ -515,10 +631,42 @@ static int gmres_ensure(maus_ctx* ctx, long long n, long long C, GmresWs** out) 
     // and make the ranks issue different numbers of collectives
     GM_ALLOC(ws->vc, vec); GM_ALLOC(ws->zc, vec);
 #undef GM_ALLOC
+    if (cudaHostAlloc((void**)&ws->host_poll, 2 * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ws->poll_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ws->poll_ev[1], cudaEventDisableTiming) != cudaSuccess) {
+        ctx->gmres = ws; ws->bytes = total; ctx->bytes_held += (long long)total; maus_gmres_free(ctx);
+        return maus_fail(ctx, MAUS_E_NOMEM, "GMRES poll buffers");
+    }
     ws->bytes = total;
     ctx->bytes_held += (long long)total;
     ctx->gmres = ws;
     *out = ws;
+    return MAUS_OK;
+}
+
+static int launch_arnoldi_cluster(maus_ctx* ctx, GmresWs* ws, long long n, int m, int col, long long C, cudaStream_t st) {
+    int ept = 1;
+    while ((n + ept - 1) / ept > (long long)GA_MAXC * GA_NT) ept *= 2;       // n <= 32768 -> ept <= 16
+    const int nc = (int)(((n + ept - 1) / ept + GA_NT - 1) / GA_NT);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(C * nc), 1, 1);
+    cfg.blockDim = dim3(GA_NT, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cplx* z = ws->z; cplx* Vk = ws->Vk; const cplx* minv = ws->minv; GmresCand* cand = ws->cand; int* counters = ws->counters;
+    cudaError_t e;
+    switch (ept) {
+        case 1: e = cudaLaunchKernelEx(&cfg, gm_arnoldi_cluster_kernel<1>, z, Vk, minv, cand, n, m, col, counters); break;
+        case 2: e = cudaLaunchKernelEx(&cfg, gm_arnoldi_cluster_kernel<2>, z, Vk, minv, cand, n, m, col, counters); break;
+        case 4: e = cudaLaunchKernelEx(&cfg, gm_arnoldi_cluster_kernel<4>, z, Vk, minv, cand, n, m, col, counters); break;
+        case 8: e = cudaLaunchKernelEx(&cfg, gm_arnoldi_cluster_kernel<8>, z, Vk, minv, cand, n, m, col, counters); break;
+        default: e = cudaLaunchKernelEx(&cfg, gm_arnoldi_cluster_kernel<16>, z, Vk, minv, cand, n, m, col, counters); break;
+    }
+    MAUS_CUDA(ctx, e);
     return MAUS_OK;
 }
 
@@ -539,6 +687,10 @@ int gmres_core(maus_ctx* ctx, const GmresOperator& op, long long C, const cplx* 
     // the random perturbation only matters once 0.15*psi exceeds rounding of the matvec (~1e-17 * max|a_ij|)
     const double gate = 1e-17 * std::max(op.amax, 1e-300);
     const bool any_perturb = op.dense && keys && (0.15 * max_psi_host > gate);
+    // one-launch Arnoldi step for vectors that fit a cluster (MAUS_GMRES_CLUSTER=0: the multi-launch path, A/B measurements)
+    static int cluster_env = -1;
+    if (cluster_env < 0) { const char* e = getenv("MAUS_GMRES_CLUSTER"); cluster_env = e ? (atoi(e) != 0) : 1; }
+    const bool use_cluster = cluster_env && !op.reduce_partials && n <= (long long)GA_MAXC * GA_NT * 16;
     int host_counters[2];
     // row-sharded mode: every rank holds a slice of each vector, so the per-block partial sums are combined over the ranks
     // (one kernel over NVLink peer memory, rowshard.cu) before the scalar kernels consume them
@@ -599,26 +751,41 @@ int gmres_core(maus_ctx* ctx, const GmresOperator& op, long long C, const cplx* 
         gm_start_scalar_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, ws->counters);
         gm_store_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->cand, n, m, ws->Vk, 0, nblk, 1);
         ctx->launches += 3;
-        for (int col = 0; col < m; ++col) {
+        // The host only needs the number of candidates still inside their Arnoldi loop to END the loop early.  It is read with a
+        // lag of one iteration (the copy of iteration j is waited for after iteration j + 1 has been queued), so the stream
+        // never drains between iterations; the kernels of a surplus iteration find no inner-active candidate and do nothing.
+        int pending = -1;                                     // slot of host_poll that is in flight
+        bool all_left = false;
+        for (int col = 0; col < m && !all_left; ++col) {
             if ((rc = matvec(ws->Vk + (long long)col * n, (long long)(m + 1) * n))) return rc;
-            gm_post_matvec_kernel<<<gridv, GM_NT, 0, st>>>(ws->z, ws->Vk, ws->minv, ws->cand, n, m, col, ws->w, ws->partial, nblk);
-            GM_SYNC();
-            gm_h0_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk);
-            for (int k = 0; k <= col; ++k) {
-                gm_mgs_pass_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->Vk, ws->cand, n, m, k, 0, ws->partial, nblk);
-                GM_SYNC();
-                gm_mgs_scalar_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, k);
-            }
-            gm_mgs_pass_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->Vk, ws->cand, n, m, col + 1, 1, ws->partial, nblk);
-            GM_SYNC();
             MAUS_CUDA(ctx, cudaMemsetAsync(ws->counters, 0, sizeof(int), st));
-            gm_hess_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, m, ws->counters);
-            gm_store_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->cand, n, m, ws->Vk, 1, nblk, 1);
-            gm_advance_kernel<<<gridc, 128, 0, st>>>(ws->cand, (int)C);
-            ctx->launches += 6 + 2 * (col + 1);
-            MAUS_CUDA(ctx, cudaMemcpyAsync(host_counters, ws->counters, sizeof(int), cudaMemcpyDeviceToHost, st));
-            MAUS_CUDA(ctx, cudaStreamSynchronize(st));
-            if (host_counters[0] == 0) break;                // every candidate left its inner loop
+            if (use_cluster) {
+                if ((rc = launch_arnoldi_cluster(ctx, ws, n, m, col, C, st))) return rc;
+                ctx->launches += 1;
+            } else {
+                gm_post_matvec_kernel<<<gridv, GM_NT, 0, st>>>(ws->z, ws->Vk, ws->minv, ws->cand, n, m, col, ws->w, ws->partial, nblk);
+                GM_SYNC();
+                gm_h0_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk);
+                for (int k = 0; k <= col; ++k) {
+                    gm_mgs_pass_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->Vk, ws->cand, n, m, k, 0, ws->partial, nblk);
+                    GM_SYNC();
+                    gm_mgs_scalar_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, k);
+                }
+                gm_mgs_pass_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->Vk, ws->cand, n, m, col + 1, 1, ws->partial, nblk);
+                GM_SYNC();
+                gm_hess_kernel<<<gridc, 128, 0, st>>>(ws->cand, ws->partial, (int)C, nblk, m, ws->counters);
+                gm_store_kernel<<<gridv, GM_NT, 0, st>>>(ws->w, ws->cand, n, m, ws->Vk, 1, nblk, 1);
+                gm_advance_kernel<<<gridc, 128, 0, st>>>(ws->cand, (int)C);
+                ctx->launches += 6 + 2 * (col + 1);
+            }
+            const int slot = col & 1;
+            MAUS_CUDA(ctx, cudaMemcpyAsync(&ws->host_poll[slot], ws->counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+            MAUS_CUDA(ctx, cudaEventRecord(ws->poll_ev[slot], st));
+            if (pending >= 0) {
+                MAUS_CUDA(ctx, cudaEventSynchronize(ws->poll_ev[pending]));
+                if (ws->host_poll[pending] == 0) all_left = true;          // every candidate had left one iteration ago
+            }
+            pending = slot;
         }
         gm_solve_y_kernel<<<gridc, 128, 0, st>>>(ws->cand, (int)C);
         gm_update_x_kernel<<<gridv, GM_NT, 0, st>>>(ws->x, ws->Vk, ws->cand, n, m, nblk);

@@ -78,8 +78,10 @@ struct PanelSlot {
     cplx data[IB];     // that row's inner-block entries
 };
 
-template <int R, int IB, int PANEL_NT>
-__global__ void __launch_bounds__(PANEL_NT, (PANEL_NT <= 256) ? 2 : 1)
+// MINB = CTAs per SM the register allocation is held to, UW = columns per step of the in-leaf rank-IB update (the update keeps
+// 2 UW columns of prefetch + UW in flight per row: UW = 4 needs ~128 registers, UW = 2 fits 64)
+template <int R, int IB, int PANEL_NT, int MINB, int UW>
+__global__ void __launch_bounds__(PANEL_NT, MINB)
 lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pairs, int* info) {
     cg::cluster_group cluster = cg::this_cluster();
     const int NC = (int)cluster.num_blocks();
@@ -244,31 +246,31 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
 #pragma unroll
                     for (int j = 0; j < IB; ++j) l[j] = (j < ibw) ? P[row[q] + (long long)(ib0 + j) * ld] : cmake(0.0, 0.0);
                     cplx* prow = P + row[q] + (long long)(ib0 + ibw) * ld;
-                    const int rest4 = rest & ~3;
-                    // software pipeline two groups of four columns deep (three measured no better): the loads of columns c + 4 .. c + 11 are in flight
-                    // while columns c .. c + 3 are updated (the rows come from L2 / HBM, ~1 us away)
-                    cplx n0[4], n1[4];
+                    const int rest4 = (rest / UW) * UW;
+                    // software pipeline two groups of UW columns deep (three measured no better): the loads of columns c + UW .. c + 3 UW - 1
+                    // are in flight while columns c .. c + UW - 1 are updated (the rows come from L2 / HBM, ~1 us away)
+                    cplx n0[UW], n1[UW];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < UW; ++u) {
                         n0[u] = (rest4 > 0) ? prow[(long long)u * ld] : cmake(0.0, 0.0);
-                        n1[u] = (rest4 > 4) ? prow[(long long)(4 + u) * ld] : cmake(0.0, 0.0);
+                        n1[u] = (rest4 > UW) ? prow[(long long)(UW + u) * ld] : cmake(0.0, 0.0);
                     }
 #pragma unroll 1
-                    for (int c = 0; c < rest4; c += 4) {
-                        cplx x[4];
+                    for (int c = 0; c < rest4; c += UW) {
+                        cplx x[UW];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { x[u] = n0[u]; n0[u] = n1[u]; }
-                        if (c + 8 < rest4) {
+                        for (int u = 0; u < UW; ++u) { x[u] = n0[u]; n0[u] = n1[u]; }
+                        if (c + 2 * UW < rest4) {
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) n1[u] = prow[(long long)(c + 8 + u) * ld];
+                            for (int u = 0; u < UW; ++u) n1[u] = prow[(long long)(c + 2 * UW + u) * ld];
                         }
 #pragma unroll
                         for (int j = 0; j < IB; ++j) {
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) cfms(x[u], l[j], U12[j][c + u]);
+                            for (int u = 0; u < UW; ++u) cfms(x[u], l[j], U12[j][c + u]);
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) prow[(long long)(c + u) * ld] = x[u];
+                        for (int u = 0; u < UW; ++u) prow[(long long)(c + u) * ld] = x[u];
                     }
                     for (int c = rest4; c < rest; ++c) {
                         cplx x = prow[(long long)c * ld];
@@ -526,7 +528,7 @@ cudaError_t lu_build_aug(cplx* W, long long strideW, int n, int batch, const cpl
     return cudaGetLastError();
 }
 
-template <int R, int IB, int PANEL_NT>
+template <int R, int IB, int PANEL_NT, int MINB, int UW>
 static cudaError_t launch_panel(cplx* W, long long strideW, int n, int k0, int jb, int batch, LuPairs* pairs, int* info,
                                 int nc, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
@@ -538,7 +540,7 @@ static cudaError_t launch_panel(cplx* W, long long strideW, int n, int k0, int j
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, lu_panel_kernel<R, IB, PANEL_NT>, W, strideW, n, k0, jb, pairs, info);
+    return cudaLaunchKernelEx(&cfg, lu_panel_kernel<R, IB, PANEL_NT, MINB, UW>, W, strideW, n, k0, jb, pairs, info);
 }
 
 cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batch, LuPairs* pairs, int* info,
@@ -555,10 +557,14 @@ cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batc
     //   B: NT 256, R 2, IB 8  -> <= 4096 rows, two CTAs of different clusters share an SM so one cluster's barrier
     //                            latency hides behind the other's arithmetic (large batches are SM-time bound)
     //   C: NT 512, R 2, IB 8  -> <= 8192 rows
+    //   D: NT 512, R 1, IB 8, 64 registers -> <= 4096 rows, two 512-thread CTAs per SM: the same rows per SM as B with twice
+    //                            the warps (32 per SM), half the serial work per thread and column
+    //   E: NT 256, R 2, IB 8, 80 registers -> three CTAs per SM
     int mode = (batch >= 12) ? 1 : 0;
     if (force_r == 1) mode = 0; else if (force_r == 2) mode = 2; else if (force_r == 3) mode = 1;
+    else if (force_r == 4) mode = 3; else if (force_r == 5) mode = 4;
     if (m > PANEL_MAXC * 512) mode = 2;
-    const int rows_per_cta = (mode == 0) ? 512 : (mode == 1 ? 512 : 1024);
+    const int rows_per_cta = (mode == 2) ? 1024 : 512;
     // cluster size = exactly the CTAs the panel's rows need (1..8, not rounded up to a power of two: a CTA without rows
     // would still occupy its half SM for the whole column loop)
     static int pow2 = -1;
@@ -566,9 +572,11 @@ cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batc
     int need = (m + rows_per_cta - 1) / rows_per_cta;
     int nc = need < 1 ? 1 : need;
     if (pow2) { nc = 1; while (nc < need) nc <<= 1; }
-    if (mode == 0) return launch_panel<1, 16, 512>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
-    if (mode == 1) return launch_panel<2, 8, 256>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
-    return launch_panel<2, 8, 512>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+    if (mode == 0) return launch_panel<1, 16, 512, 1, 4>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+    if (mode == 1) return launch_panel<2, 8, 256, 2, 4>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+    if (mode == 3) return launch_panel<1, 8, 512, 2, 2>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+    if (mode == 4) return launch_panel<2, 8, 256, 3, 2>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
+    return launch_panel<2, 8, 512, 1, 4>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
 }
 
 cudaError_t lu_permute_rows(cplx* W, long long strideW, int n, int k0, int colstart, int batch, const LuPairs* pairs,

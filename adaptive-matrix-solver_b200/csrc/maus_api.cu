@@ -421,13 +421,14 @@ int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cpl
             p.B = V; p.ldb = ldv; p.strideB = 0;
             p.C = Y; p.ldc = ldy; p.strideC = 0;
             p.M = (int)n; p.N = (int)C; p.K = (int)n; p.batch = 1; p.beta = 0; p.negate = 0;
-            // skinny product (few row tiles): pick the kernel with the smaller (rounds over the SMs) x (work per tile):
-            // 4-product kernel 128 x 64 tiles at 8 flops, 3M kernel 128 x 48 tiles at 6 flops per complex multiply-add
+            // skinny product (few row tiles): pick the tiling with the smallest (rounds over the SMs) x (work per tile):
+            // 4-product kernel 128 x 64 tiles at 8 flops, 3M kernel 128 x 48 or 128 x 32 tiles at 6 flops per complex multiply-add
             {
                 const long long sms = ctx->sm_count > 0 ? ctx->sm_count : MAUS_SM_COUNT_B200;
-                const long long mt = (n + 127) / 128, t4 = mt * ((C + 63) / 64), t3 = mt * ((C + 47) / 48);
-                const long long est4 = ((t4 + sms - 1) / sms) * 64 * 8, est3 = ((t3 + sms - 1) / sms) * 48 * 6;
-                p.algo3m = (lu_use_3m() && est3 < est4) ? 1 : 0;
+                const long long mt = (n + 127) / 128;
+                auto est = [&](long long tn, long long flops) { return ((mt * ((C + tn - 1) / tn) + sms - 1) / sms) * tn * flops; };
+                const long long est4 = est(64, 8), est48 = est(48, 6), est32 = est(32, 6);
+                if (lu_use_3m() && std::min(est48, est32) < est4) { p.algo3m = 1; p.tile_n = (est32 < est48) ? 32 : 48; }
             }
             int h = prof_begin(ctx, MAUS_PROF_MATVEC_GEMM, 8.0 * n * (double)n * C);
             MAUS_CUDA(ctx, zgemm_dmma_launch(p, ctx->stream));
@@ -871,7 +872,8 @@ static int zgemm_host(maus_ctx* ctx, const char* who, int M, int N, int K, int b
         p.B = dB; p.ldb = K; p.strideB = (long long)K * N;
         p.C = dC; p.ldc = M; p.strideC = (long long)M * N;
         p.M = M; p.N = N; p.K = K; p.batch = batch; p.beta = beta; p.negate = negate;
-        p.algo3m = (algo == 2) ? 1 : 0;                     // 2: the three-product (3M) tensor-pipe kernel of the LU updates
+        p.algo3m = (algo >= 2) ? 1 : 0;                     // 2: the three-product (3M) tensor-pipe kernel of the LU updates
+        p.tile_n = (algo == 3) ? 32 : 0;                    // 3: its 128 x 32 tile variant (skinny batched A*V)
         e = algo ? zgemm_dmma_launch(p, st) : zgemm_simple_launch(p, st);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(Cm, dC, bc, cudaMemcpyDeviceToHost, st);

@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(Cfg<TM, AB>::NTHREADS, Cfg<TM, AB>::CTAS_PER_S
 //   (72 f64 accumulators) + 1 producer warp (same TMA bulk-copy rings as above).  Column strides 130 / 36 complex make
 //   the 128-bit fragment loads conflict free per quarter warp.  C is added in the epilogue (accumulators start at 0).
 namespace m3 {
-constexpr int TM = 128, TN = 48;
-constexpr int QA = 4, QB = 3, NWM = 4, NWN = 2;
+constexpr int TM = 128;
+constexpr int QA = 4, NWM = 4, NWN = 2;          // QB (m8n8 tiles per warp along n) is a Pipe parameter: CTA tile 128 x (16 QB)
 // Register budget: the register file is split per SM sub-partition (16 K registers each), so a 9th warp would cap every
 // thread at 168 registers.  The CTA is launched as three warpgroups (2 consumer + 1 producer warpgroup of which one warp
 // works) at 168 registers, then the consumers grow to 232 and the producer warpgroup shrinks to 40 (setmaxnreg):
@@ -281,10 +281,12 @@ constexpr int QA = 4, QB = 3, NWM = 4, NWN = 2;
 constexpr int NCONS = NWM * NWN, NTHREADS = (NCONS + 4) * 32;
 constexpr int REG_CONSUMER = 232, REG_PRODUCER = 40;
 static_assert(NCONS == 8, "two consumer warpgroups");
-static_assert(NWM * QA * 8 == TM && NWN * QB * 8 == TN, "warp grid must cover the CTA tile");
-// pipeline shape: A slabs of KC complex k (KC bulk copies of TM*16 B), B slabs of KCB complex k (TN copies of KCB*16 B)
-template <int KC_, int STAGES_, int KCB_, int BSTAGES_> struct Pipe {
-    static constexpr int KC = KC_, STAGES = STAGES_, KCB = KCB_, BSTAGES = BSTAGES_;
+static_assert(NWM * QA * 8 == TM, "warp grid must cover the CTA tile");
+// pipeline shape: A slabs of KC complex k (KC bulk copies of TM*16 B), B slabs of KCB complex k (TN copies of KCB*16 B);
+// QB = 3: 128 x 48 tiles (LU trailing updates), QB = 2: 128 x 32 tiles (skinny batched A*V: N = 64 / 128 candidates are whole
+// multiples of 32 but leave a 16-wide remainder tile at 48)
+template <int KC_, int STAGES_, int KCB_, int BSTAGES_, int QB_ = 3> struct Pipe {
+    static constexpr int KC = KC_, STAGES = STAGES_, KCB = KCB_, BSTAGES = BSTAGES_, QB = QB_, TN = NWN * QB_ * 8;
     static constexpr int LDSA = TM + 2, LDSB = KCB + 4;        // strides = 2 / 4 (mod 8) complex: conflict-free LDS.128
     static constexpr int A_STAGE = KC * LDSA, B_STAGE = TN * LDSB;
     // result staging tile [TN][LDSC]: column stride = 1 (mod 4) complex makes the fragment-order STS.128 conflict free
@@ -298,8 +300,8 @@ template <int KC_, int STAGES_, int KCB_, int BSTAGES_> struct Pipe {
 
 template <class PP>
 __global__ void __launch_bounds__(m3::NTHREADS, 1) zgemm3m_dmma_kernel(ZgemmParams p) {
-    constexpr int TM = m3::TM, TN = m3::TN, KC = PP::KC, STAGES = PP::STAGES, KCB = PP::KCB, BSTAGES = PP::BSTAGES, LDSA = PP::LDSA,
-                  LDSB = PP::LDSB, A_STAGE = PP::A_STAGE, B_STAGE = PP::B_STAGE, QA = m3::QA, QB = m3::QB, NWN = m3::NWN,
+    constexpr int TM = m3::TM, TN = PP::TN, KC = PP::KC, STAGES = PP::STAGES, KCB = PP::KCB, BSTAGES = PP::BSTAGES, LDSA = PP::LDSA,
+                  LDSB = PP::LDSB, A_STAGE = PP::A_STAGE, B_STAGE = PP::B_STAGE, QA = m3::QA, QB = PP::QB, NWN = m3::NWN,
                   NCONS = m3::NCONS, LDSC = PP::LDSC, C_STAGE = PP::C_STAGE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* sA = reinterpret_cast<cplx*>(smem_raw);
@@ -578,7 +580,7 @@ static cudaError_t launch_3m_cfg(const ZgemmParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const long long ntiles = (long long)((p.M + m3::TM - 1) / m3::TM) * ((p.N + m3::TN - 1) / m3::TN) * p.batch;
+    const long long ntiles = (long long)((p.M + m3::TM - 1) / m3::TM) * ((p.N + PP::TN - 1) / PP::TN) * p.batch;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = MAUS_SM_COUNT_B200; }
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);          // persistent: one CTA per SM
@@ -587,6 +589,7 @@ static cudaError_t launch_3m_cfg(const ZgemmParams& p, cudaStream_t stream) {
 }
 
 static cudaError_t launch_3m(const ZgemmParams& p, cudaStream_t stream) {
+    if (p.tile_n == 32) return launch_3m_cfg<m3::Pipe<16, 2, 32, 2, 2>>(p, stream);
     static int cfg = -1;
     if (cfg < 0) { const char* e = getenv("MAUS_3M_CFG"); cfg = e ? atoi(e) : 0; }
     switch (cfg) {

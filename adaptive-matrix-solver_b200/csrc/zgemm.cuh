@@ -10,6 +10,7 @@ struct ZgemmParams {
     int beta;      // 0: C = s*A*B        1: C = C + s*A*B
     int negate;    // s = -1 when set, else +1
     int algo3m;    // 1: three-real-product complex arithmetic (6 instead of 8 flops per complex FMA; LU updates)
+    int tile_n;    // 3M kernel only: 0 / 48 = 128 x 48 CTA tiles, 32 = 128 x 32 tiles (skinny products whose N is a multiple of 32)
 };
 
 // Tensor-pipe kernel (any M, N, K >= 1).  In-place use (C == B) is supported for M <= 128: it is routed to the 128-row tile configuration so one CTA owns all rows of its columns.

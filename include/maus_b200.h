@@ -206,7 +206,8 @@ int maus_rs_step(maus_ctx* ctx, int64_t C, int problem_type, int phases, double*
 
 /* debug / parity: C = beta*C + s*A*B on column-major complex128 host matrices (A: M x K, B: K x N, C: M x N,
  * `batch` of each, densely packed) through the tensor-pipe kernel (use_dmma = 1; 2 = the three-real-product
- * variant used by the LU trailing updates) or the plain FP64-FMA kernel (use_dmma = 0). */
+ * variant used by the LU trailing updates; 3 = its 128 x 32 tile shape used for skinny batched A*V) or the plain FP64-FMA
+ * kernel (use_dmma = 0). */
 int maus_debug_zgemm(maus_ctx* ctx, int M, int N, int K, int batch, const double* A, const double* B, double* C,
                      int beta, int negate, int use_dmma);
 

@@ -37,6 +37,9 @@ def test_zgemm_dmma_matches_numpy(eng, M, N, K, batch, beta, negate):
     # the LU's 3M kernel (three real products): normwise the same bound, a different rounding pattern
     out3 = eng.debug_zgemm(Acm, Bcm, Ccm, beta=beta, negate=negate, use_dmma=2).transpose(0, 2, 1)
     assert np.abs(out3 - ref).max() <= 2e-14 * scale
+    # ... and its 128 x 32 tile shape (skinny batched A*V); same products, same accumulation order per element
+    out4 = eng.debug_zgemm(Acm, Bcm, Ccm, beta=beta, negate=negate, use_dmma=3).transpose(0, 2, 1)
+    assert np.array_equal(out4, out3)
 
 
 @pytest.mark.parametrize("n", [1, 2, 5, 8, 16, 100, 127, 128, 129, 256, 300, 520])
