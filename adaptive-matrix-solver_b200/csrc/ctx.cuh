@@ -62,6 +62,7 @@ struct maus_ctx {
     cplx* Linv = nullptr;
     cplx* Rcm = nullptr;             // debug: host-supplied perturbation (column-major)
     long long ws_limit = 0;
+    bool lu_conj_transpose = false;  // maus_lu_solve factors A^H instead of A (condition estimate, diag.cu)
 
     // GMRES workspace (gmres.cu)
     void* gmres = nullptr;

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) lu_build_aug_kernel(cplx* W, long long st
                                                            const double* __restrict__ psi,
                                                            const unsigned long long* __restrict__ keys,
                                                            const cplx* __restrict__ R_cm, const cplx* __restrict__ rhs,
-                                                           long long rhs_stride, int always_draw) {
+                                                           long long rhs_stride, int always_draw, int conj_in) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i >= n) return;
@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(256) lu_build_aug_kernel(cplx* W, long long st
         for (int b = 0; b < batch; ++b) W[b * strideW + off] = rhs[b * rhs_stride + i];
         return;
     }
-    const cplx a = Acm[off];
+    cplx a = Acm[off];
+    if (conj_in) a.y = -a.y;
     for (int b = 0; b < batch; ++b) {
         // same association as the reference: T = A - lambda*I (AMS:270); reg = psi*I + perturb (AMS:50); H = T + reg (AMS:52)
         cplx h = a;
@@ -520,11 +521,11 @@ __global__ void __launch_bounds__(BS_NT) lu_backsolve_kernel(const cplx* __restr
 // ------------------------------------------------------------------------------------------------------------
 cudaError_t lu_build_aug(cplx* W, long long strideW, int n, int batch, const cplx* Acm, const cplx* sigma,
                          const double* psi, const unsigned long long* keys, const cplx* R_cm, const cplx* rhs,
-                         long long rhs_stride, cudaStream_t stream) {
+                         long long rhs_stride, cudaStream_t stream, int conj_in) {
     dim3 grid((n + 255) / 256, n + 1, 1);
     static int always_draw = -1;      // MAUS_PHILOX_ALWAYS=1 disables the exact skip (used by the bit-identity test)
     if (always_draw < 0) { const char* e = getenv("MAUS_PHILOX_ALWAYS"); always_draw = (e && atoi(e)) ? 1 : 0; }
-    lu_build_aug_kernel<<<grid, 256, 0, stream>>>(W, strideW, n, batch, Acm, sigma, psi, keys, R_cm, rhs, rhs_stride, always_draw);
+    lu_build_aug_kernel<<<grid, 256, 0, stream>>>(W, strideW, n, batch, Acm, sigma, psi, keys, R_cm, rhs, rhs_stride, always_draw, conj_in);
     return cudaGetLastError();
 }
 

@@ -16,9 +16,10 @@ struct LuPairs {
 
 // W: batch matrices, column-major, ld = n, n+1 columns (last column = right-hand side), strideW elements apart.
 // H_b = Acm + (psi_b - sigma_b) I + R_b  with R_b from Philox (key_b) or R_host (batch must be 1) or none.
+// conj_in: the entries of Acm are conjugated while they are read (Acm = the row-major copy + conj_in = A^H, diag.cu).
 cudaError_t lu_build_aug(cplx* W, long long strideW, int n, int batch, const cplx* Acm, const cplx* sigma,
                          const double* psi, const unsigned long long* keys, const cplx* R_cm,
-                         const cplx* rhs, long long rhs_stride, cudaStream_t stream);
+                         const cplx* rhs, long long rhs_stride, cudaStream_t stream, int conj_in = 0);
 
 // one panel step k0: factor W[k0:n, k0:k0+jb] with implicit partial pivoting, emit the row permutation.
 cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batch, LuPairs* pairs, int* info,

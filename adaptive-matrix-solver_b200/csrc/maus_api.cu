@@ -501,8 +501,9 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
     for (long long c0 = 0; c0 < C; c0 += wb) {
         const int nb = (int)std::min<long long>(wb, C - c0);
         int hb = prof_begin(ctx, MAUS_PROF_BUILD, 16.0 * n * (double)n * (nb + 1));
-        MAUS_CUDA(ctx, lu_build_aug(ctx->W, strideW, n, nb, s.cm, sigma + c0, psi + c0, keys ? keys + c0 : nullptr, Rcm,
-                                    rhs + c0 * rhs_stride, rhs_stride, st));
+        MAUS_CUDA(ctx, lu_build_aug(ctx->W, strideW, n, nb, ctx->lu_conj_transpose ? s.rm : s.cm, sigma + c0, psi + c0,
+                                    keys ? keys + c0 : nullptr, Rcm, rhs + c0 * rhs_stride, rhs_stride, st,
+                                    ctx->lu_conj_transpose ? 1 : 0));
         prof_end(ctx, hb);
         MAUS_CUDA(ctx, cudaMemsetAsync(ctx->info, 0, (size_t)nb * sizeof(int), st));
         ctx->launches += 1;

@@ -282,6 +282,22 @@ class MausEngine:
             self._check(self._lib.maus_gram(self._h, V.shape[0], V.shape[1], _dp(V), _dp(G)))
         return G
 
+    # -- set-up diagnostics (AMS:374-404) -----------------------------------------------------------------------
+    def diag_dense(self, rtol=1e-5, atol=1e-8):
+        """(non-zeros, is_hermitian, is_complex_symmetric) of the resident dense matrix: np.count_nonzero + the two np.allclose
+        tests of AMS:381-385 in one device pass."""
+        nz, h, s_ = C.c_int64(), C.c_int32(), C.c_int32()
+        self._check(self._lib.maus_diag_dense(self._h, float(rtol), float(atol), C.byref(nz), C.byref(h), C.byref(s_)))
+        return int(nz.value), bool(h.value), bool(s_.value)
+
+    def cond2_estimate(self, power_iters=40, inverse_iters=8, start=None):
+        """(sigma_max, sigma_min, lu_status) of the resident dense matrix (replaces the full SVD behind np.linalg.cond, AMS:400)"""
+        a, b, st = C.c_double(), C.c_double(), C.c_int32()
+        start = None if start is None else _as_c128(start, (self.n,))
+        self._check(self._lib.maus_cond2_estimate(self._h, int(power_iters), int(inverse_iters), _dp(start), C.byref(a),
+                                                  C.byref(b), C.byref(st)))
+        return a.value, b.value, int(st.value)
+
     # -- SVD power-sweep branch (AMS:227-255, 300-301) -------------------------------------------------------
     def svd_set_matrix(self, A):
         A = _as_c128(A)

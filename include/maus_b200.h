@@ -159,6 +159,20 @@ int maus_svd_residual(maus_ctx* ctx, int64_t C, const double* U, const double* V
  * (Adaptive_Matrix_Solver_0.1.py:436, 450, 515, 520) by one device pass. */
 int maus_gram(maus_ctx* ctx, int64_t C, int64_t n, const double* V, double* G_out);
 
+/* ---- set-up diagnostics (MAUS_Solver._diagnose_matrix_initial, Adaptive_Matrix_Solver_0.1.py:374-404) ----- */
+/* On the dense matrix resident in slot 0: number of non-zero entries (np.count_nonzero, AMS:381) and the two np.allclose tests
+ * of AMS:384-385 -- is_hermitian = all(isclose(A, A^H)), is_complex_symmetric = all(isclose(A, A^T)) with numpy's element
+ * test |a - b| <= atol + rtol |b| (numpy defaults: rtol 1e-5, atol 1e-8). */
+int maus_diag_dense(maus_ctx* ctx, double rtol, double atol, int64_t* nonzeros, int32_t* is_hermitian,
+                    int32_t* is_complex_symmetric);
+/* 2-norm condition number estimate replacing np.linalg.cond (AMS:400, a full SVD): sigma_max by `power_iters` power sweeps on
+ * A^H A (HBM-bound matvecs), sigma_min by `inverse_iters` inverse sweeps through the batched LU (A^H y = x, A z = y).  Both are
+ * one-sided (sigma_max from below, sigma_min from above): sigma_max / sigma_min <= cond_2(A).  sigma_min = 0 and lu_status != 0
+ * when the factorisation met a zero pivot / non-finite solve (numerically singular).  `start`: optional start vector [n]
+ * complex128.  Uses the population buffers as scratch: call it before the candidate vectors are uploaded. */
+int maus_cond2_estimate(maus_ctx* ctx, int power_iters, int inverse_iters, const double* start, double* sigma_max,
+                        double* sigma_min, int32_t* lu_status);
+
 /* ---- Hermitian shortcut --------------------------------------------------------------------------- */
 /* P[c][i] = <e_i, v_c> for the m eigenvectors E = [e_0 .. e_{m-1}] of sla.eigh and C candidate vectors: the similarity scores
  * |v^H E| of Adaptive_Matrix_Solver_0.1.py:165 for the whole population as one tensor-pipe GEMM.  Ec = conj(E) in C order

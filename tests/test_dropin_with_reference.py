@@ -176,3 +176,24 @@ def test_generation_with_device_dedup_equals_generation_without():
     assert a.num_distinct_converged_solutions >= 1
     for ca, cb in zip(a.candidates, b_.candidates):
         assert ca.lambda_k == cb.lambda_k and np.array_equal(ca.v_k, cb.v_k)
+
+
+def test_initial_strategy_mirrors_the_reference_for_its_own_scenarios():
+    """diagnostics.initial_strategy (AMS:405-421 as a pure function) against the strategy the REAL MAUS_Solver.__init__ derives,
+    for matrices on each side of the cond thresholds and every problem type."""
+    from adaptive_matrix_solver_b200.diagnostics import initial_strategy
+    ams = load_reference(gmres_shim=True, name="ams_diag")
+    rng = np.random.default_rng(0)
+    G = rng.standard_normal((40, 40)) + 1j * rng.standard_normal((40, 40))
+    U, _, Vh = np.linalg.svd(G)
+    mats = [G, (U * np.logspace(0, -8, 40)) @ Vh, (U * np.logspace(0, -13, 40)) @ Vh, (U * np.r_[np.ones(39), 0.0]) @ Vh]
+    for M in mats:
+        for pt in (ams.ProblemType.EIGENVALUE, ams.ProblemType.SOLVE_LINEAR_SYSTEM, ams.ProblemType.SVD):
+            np.random.seed(1); random.seed(1)
+            b = np.ones(40, dtype=np.complex128) if pt == ams.ProblemType.SOLVE_LINEAR_SYSTEM else None
+            s = quiet(ams.MAUS_Solver, M, problem_type=pt, b_vector=b, initial_num_candidates=2, global_convergence_tol=1e-8)
+            strat, know = initial_strategy(s.diag_info, pt.name, 1e-8)
+            for k, v in strat.items():
+                assert s.strat_params[k] == v, (pt, k)
+            for k, v in know.items():
+                assert s.problem_knowledge[k] == v, (pt, k)

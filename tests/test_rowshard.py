@@ -56,7 +56,7 @@ def eng():
 
 
 @pytest.mark.gpu
-def test_world1_matches_replicated_operator_bitwise(eng):
+def test_world1_matches_replicated_operator(eng):
     from adaptive_matrix_solver_b200 import _abi
     from adaptive_matrix_solver_b200.rowshard import RowShardedOperator
     from adaptive_matrix_solver_b200.workloads import k5_sparse
@@ -75,7 +75,9 @@ def test_world1_matches_replicated_operator_bitwise(eng):
     eng.set_matrix(A)
     X2, st2, it2 = eng.solve_shifted(sigma, psi, rng_key=None, method=_abi.METHOD_GMRES, RHS=RHS)
     assert np.array_equal(st, st2) and np.array_equal(it, it2)
-    assert np.array_equal(X, X2)                      # same kernels, same reduction order
+    # same matvec kernel; the replicated path runs the one-launch cluster Arnoldi step at this order (another, equally fixed,
+    # summation order of the dot products), so the solutions agree to rounding, not bit for bit
+    assert np.abs(X - X2).max() <= 1e-12 * np.abs(X2).max()
     for c in range(C):
         H = sp.csc_matrix(A - sigma[c] * sp.eye(n, format="csc") + psi[c] * sp.identity(n, format="csc"))
         xr, info, nit = scipy_gmres(H, RHS[c])
