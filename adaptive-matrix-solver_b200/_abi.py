@@ -15,7 +15,7 @@ SLOT_CURRENT, SLOT_CTOR = 0, 1
 
 EXPORTS = [
     "maus_create", "maus_destroy", "maus_last_error", "maus_set_workspace_limit", "maus_info", "maus_alloc_pinned",
-    "maus_free_pinned", "maus_set_dense", "maus_set_csc", "maus_set_rhs", "maus_upload_vectors",
+    "maus_free_pinned", "maus_set_dense", "maus_add_dense_form", "maus_set_csc", "maus_set_rhs", "maus_upload_vectors",
     "maus_download_vectors", "maus_download_vector_range", "maus_rq", "maus_solve_shifted", "maus_solve_with_R", "maus_mix_residual",
     "maus_residual", "maus_step", "maus_launch_count", "maus_profile_reset", "maus_profile_read", "maus_profile_read_kind", "maus_stream", "maus_debug_zgemm", "maus_svd_set_matrix", "maus_svd_step", "maus_svd_residual",
     "maus_gram", "maus_project", "maus_diag_dense", "maus_cond2_estimate", "maus_nccl_unique_id", "maus_dist_init", "maus_dist_info", "maus_gather", "maus_set_csr_rowblock",
@@ -65,6 +65,7 @@ def load_library():
         "maus_alloc_pinned": (vp, [i64]),
         "maus_free_pinned": (None, [vp]),
         "maus_set_dense": (i32, [vp, i32, i64, dp]),
+        "maus_add_dense_form": (i32, [vp, i64, dp]),
         "maus_set_csc": (i32, [vp, i32, i64, i64, i64p, i64p, dp]),
         "maus_set_rhs": (i32, [vp, dp]),
         "maus_upload_vectors": (i32, [vp, i64, dp]),

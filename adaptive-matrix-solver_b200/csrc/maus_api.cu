@@ -278,7 +278,20 @@ extern "C" int maus_profile_read_kind(maus_ctx* ctx, int kind, double* ms, int64
 // ------------------------------------------------------------------------------------------------------------
 // problem upload
 // ------------------------------------------------------------------------------------------------------------
+static int set_dense_impl(maus_ctx* ctx, int slot, int64_t n, const double* A_rowmajor, bool keep_sparse);
+
 extern "C" int maus_set_dense(maus_ctx* ctx, int slot, int64_t n, const double* A_rowmajor) {
+    return set_dense_impl(ctx, slot, n, A_rowmajor, false);
+}
+
+// Attach the dense form of the SPARSE matrix resident in slot 0 (same order): matvecs keep using the CSR copy, the batched LU
+// becomes available as the direct-solve fallback of the retry ladder (the reference falls back to SuperLU, AMS:57, 99-102).
+extern "C" int maus_add_dense_form(maus_ctx* ctx, int64_t n, const double* A_rowmajor) {
+    if (!ctx || !ctx->slot[0].sparse || ctx->n != n) return maus_fail(ctx, MAUS_E_STATE, "maus_add_dense_form: set the sparse matrix (maus_set_csc) of the same order first");
+    return set_dense_impl(ctx, 0, n, A_rowmajor, true);
+}
+
+static int set_dense_impl(maus_ctx* ctx, int slot, int64_t n, const double* A_rowmajor, bool keep_sparse) {
     if (!ctx || !A_rowmajor || n <= 0 || slot < 0 || slot > 1) return maus_fail(ctx, MAUS_E_ARG, "maus_set_dense: bad argument");
     if (n > 0x7fffffffLL) return maus_fail(ctx, MAUS_E_ARG, "maus_set_dense: n too large");
     cudaSetDevice(ctx->device);
@@ -286,7 +299,8 @@ extern "C" int maus_set_dense(maus_ctx* ctx, int slot, int64_t n, const double* 
     if (slot == 0) { int rc = reset_for_n(ctx, n); if (rc) return rc; }
     MatrixSlot& s = ctx->slot[slot];
     MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (s.sparse) free_slot(ctx, s, n);
+    if (s.sparse && !keep_sparse) free_slot(ctx, s, n);
+    // keep_sparse: the CSR arrays stay; the diagonal / max |a_ij| below are recomputed from the dense copy (same values)
     const size_t bytes = (size_t)n * n * sizeof(cplx);
     if (!s.rm) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.rm, bytes));
     if (!s.cm) MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.cm, bytes));
@@ -409,7 +423,7 @@ int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cpl
     if (slot == 1 && !ctx->slot1_set) slot = 0;
     MatrixSlot& s = ctx->slot[slot];
     const long long n = ctx->n;
-    if (s.dense) {
+    if (s.dense && !s.sparse) {              // a sparse matrix with an attached dense copy (maus_add_dense_form) multiplies as sparse
         if (C <= 8) {
             int h = prof_begin(ctx, MAUS_PROF_MATVEC, (double)((C + 3) / 4) * 16.0 * n * n + 32.0 * n * C);
             MAUS_CUDA(ctx, vec_gemv_rowmajor(s.rm, V, ldv, Y, ldy, (int)n, (int)C, ctx->stream));

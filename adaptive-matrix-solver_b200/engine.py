@@ -39,6 +39,7 @@ class MausEngine:
         self.device = int(device)
         self.n = 0
         self.is_sparse = False
+        self.has_dense_form = False         # the batched LU can run on slot 0 (dense matrix, or sparse + attached dense form)
         self.generation = 0
         self.matrix_epoch = [0, 0]          # uploads per slot; population._MatrixCache compares it (shared-engine safety)
         self.rowshard = None                # RowShardedOperator of this context (rowshard.py), set by enable_row_sharding
@@ -150,6 +151,7 @@ class MausEngine:
                                                indices.ctypes.data_as(C.POINTER(C.c_int64)), _dp(data)))
             if slot == _abi.SLOT_CURRENT:
                 self.is_sparse = True
+                self.has_dense_form = False
         else:
             A = _as_c128(A)
             if A.ndim != 2 or A.shape[0] != A.shape[1]:
@@ -158,10 +160,17 @@ class MausEngine:
             self._check(self._lib.maus_set_dense(self._h, int(slot), n, _dp(A)))
             if slot == _abi.SLOT_CURRENT:
                 self.is_sparse = False
+                self.has_dense_form = True
         if slot == _abi.SLOT_CURRENT:
             self.n = n
             self.matrix_epoch[1] += 1       # a new slot-0 matrix may change n, which drops slot 1 on the device
         self.matrix_epoch[slot] += 1
+
+    def add_dense_form(self, A_dense):
+        """keep the sparse matrix of slot 0 for the matvecs and attach its dense form for the batched LU (ladder fallback)"""
+        A_dense = _as_c128(A_dense, (self.n, self.n))
+        self._check(self._lib.maus_add_dense_form(self._h, self.n, _dp(A_dense)))
+        self.has_dense_form = True
 
     def set_rhs(self, b):
         b = _as_c128(b, (self.n,))

@@ -67,8 +67,22 @@ def _key(cand_id, generation, attempt):
     return ((int(cand_id) & 0xffffffff) << 32) | ((int(generation) & 0xffffff) << 8) | (int(attempt) & 0xff)
 
 
+def _lu_available(engine, M=None):
+    """The direct solve of the ladder (AMS:57 / 59).  A dense matrix: the batched LU up to LU_MAX_N.  A SPARSE matrix of order
+    <= LU_MAX_N: its dense form is attached to the resident CSR copy on first need (the reference falls back to SuperLU here;
+    same x up to rounding).  Beyond LU_MAX_N there is no device direct solver: the try counts as failed (deviations)."""
+    if engine.n > LU_MAX_N:
+        return False
+    if not engine.is_sparse or getattr(engine, "has_dense_form", False):
+        return True
+    if M is not None and _is_sparse(M) and hasattr(engine, "add_dense_form"):
+        engine.add_dense_form(M.toarray())
+        return True
+    return False
+
+
 def _ladder(engine, ptype, v_or_x, lam, stuck, base_psi, max_attempts, pref, matrix_sparse_semantics, cand_id,
-            first_method_failed=True):
+            first_method_failed=True, M=None):
     """AMS:43-104 for ONE candidate whose attempt-0 try with the preferred method already failed on the device.
     Returns (x or None, num_psi_attempts)."""
     fallback = 'iterative_gmres' if pref == 'direct_solve' else 'direct_solve'
@@ -80,7 +94,7 @@ def _ladder(engine, ptype, v_or_x, lam, stuck, base_psi, max_attempts, pref, mat
             psi = psi_magnitude(base_psi, attempts, stuck)
             key = None if matrix_sparse_semantics else [_key(cand_id, engine.generation, attempts + 1)]
             m = _METHOD.get(method)
-            if m is None or (m == _abi.METHOD_LU and (engine.is_sparse or engine.n > LU_MAX_N)):
+            if m is None or (m == _abi.METHOD_LU and not _lu_available(engine, M)):
                 status = _abi.ST_ZERO_PIVOT      # no direct solver for this operator on the device: the try fails (AMS:98)
                 X = None
             else:
@@ -204,11 +218,12 @@ def step_population(candidates, M, b, strat_params, problem_knowledge, engine, c
         if gkey != 0:
             cache.ensure(engine, cands[0].problem_matrix, 1, 'sparse' if _is_sparse(cands[0].problem_matrix) else 'dense')
             res_slot = _abi.SLOT_CTOR
-        _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, res_slot)
+        _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, res_slot, M_cur=M)
     return len(gpu)
 
 
-def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, res_slot, rs=None):
+def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, res_slot, rs=None,
+                M_cur=None):
     C_ = len(cands)
     eigen = ptype == _abi.EIGENVALUE
     # the vectors travel through one page-locked staging buffer (H2D before, D2H after the fused step)
@@ -264,7 +279,7 @@ def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, 
         elif st in (_abi.ST_ZERO_PIVOT, _abi.ST_NONFINITE, _abi.ST_GMRES_NOCONV):
             # the preferred method failed at attempt 0: walk the rest of the ladder for this candidate
             x, retries = _ladder(engine, ptype, V_before[i], complex(lam[i]), int(stuck[i]), base_psi, max_retries,
-                                 pref, is_sparse, c.id)
+                                 pref, is_sparse, c.id, M=M_cur)
             if x is not None:
                 Vn, r1, mixn, st1 = engine.mix_residual(ptype, [alpha[i]], [lam[i]], res_slot=res_slot)
                 V[i] = Vn[0]

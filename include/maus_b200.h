@@ -85,6 +85,9 @@ int maus_set_dense(maus_ctx* ctx, int slot, int64_t n, const double* A_rowmajor)
 /* sparse CSC as scipy.sparse.csc_matrix holds it (AMS:358); converted once to CSR on the device. */
 int maus_set_csc(maus_ctx* ctx, int slot, int64_t n, int64_t nnz, const int64_t* colptr, const int64_t* rowidx,
                  const double* vals);
+/* attach the dense form (row-major, same order) of the SPARSE matrix resident in slot 0: matvecs keep the CSR copy, the batched LU
+ * becomes available as the direct-solve fallback of the retry ladder (the reference falls back to SuperLU, AMS:57, 99-102). */
+int maus_add_dense_form(maus_ctx* ctx, int64_t n, const double* A_rowmajor);
 /* right-hand side b of SOLVE_LINEAR_SYSTEM (AMS:346) */
 int maus_set_rhs(maus_ctx* ctx, const double* b);
 
