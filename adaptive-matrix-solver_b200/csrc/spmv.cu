@@ -1,5 +1,6 @@
 // spmv.cu -- CSR sparse matrix x candidate block (SpMM) for the sparse GMRES path (AMS:47, 57 replaced by GMRES;
 // the reference's matrix is scipy CSC, converted once to CSR at upload so that rows are contiguous).
+#include <cstdlib>
 #include "spmv.cuh"
 
 namespace {
@@ -78,43 +79,80 @@ __global__ void __launch_bounds__(256) spmm_pack_kernel(const cplx* __restrict__
 // (~32 registers: 64 warps per SM keep the index -> gather chains of 64 rows in flight).
 //   lane = CB * sub + c : sub = 0..7 walks the row's entries sub, sub + 8, ... exactly like the unpacked kernel, then the same
 //   xor tree over sub -- so every candidate's sum is accumulated in the SAME order as in csr_spmm_kernel (bit-identical results).
+// The row chain rowptr -> (index, value) -> gather -> reduce is three dependent memory round trips; with one row per lane group
+// at a time the kernel was bound by that latency (ncu, round 2: DRAM 31 %, L2 31 %, l1tex 58 % busy at 63 % occupancy).  The
+// lane groups therefore walk their rows grid-strided and SOFTWARE-PIPELINED: while the gathers of row r are in flight, the
+// (index, value) loads of the group's next row and the rowptr pair of the row after that are already issued.
 template <int CB, int SP_U>
 __global__ void __launch_bounds__(SP_NT) csr_spmm_packed_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx,
                                                                 const cplx* __restrict__ vals, const cplx* __restrict__ P,
                                                                 long long p_gstride, cplx* __restrict__ Y, long long ldy,
                                                                 long long n, int c0, int ctotal) {
     constexpr int LPR = SP_LANES * CB;                     // lanes per row
+    constexpr int GPB = SP_NT / LPR;                       // lane groups (rows in flight) per CTA
     // blockIdx.y = group of CB candidates: its interleaved copy starts p_gstride elements after the previous group's
     P += (long long)blockIdx.y * p_gstride;
     c0 += (int)blockIdx.y * CB;
     const int ncand = min(CB, ctotal - c0);
-    const long long row = ((long long)blockIdx.x * SP_NT + threadIdx.x) / LPR;
     const int l = threadIdx.x % LPR, sub = l / CB, c = l % CB;
-    cplx acc = cmake(0.0, 0.0);
-    if (row < n) {
-        const long long k1 = rowptr[row + 1];
-        for (long long kb = rowptr[row] + sub; kb < k1; kb += SP_LANES * SP_U) {
-            cplx a[SP_U]; int j[SP_U];
+    const long long stride = (long long)gridDim.x * GPB;
+    long long row = (long long)blockIdx.x * GPB + threadIdx.x / LPR;
+    auto load_entries = [&](long long k0, long long k1, cplx* a, int* j) {
 #pragma unroll
-            for (int u = 0; u < SP_U; ++u) {
-                const long long k = kb + u * SP_LANES;
-                const bool ok = k < k1;
-                a[u] = ok ? __ldcs(&vals[k]) : cmake(0.0, 0.0);       // the CB lanes of an entry read the same address (broadcast)
-                j[u] = ok ? __ldcs(&colidx[k]) : -1;
-            }
-            cplx v[SP_U];
+        for (int u = 0; u < SP_U; ++u) {
+            const long long k = k0 + sub + u * SP_LANES;
+            const bool ok = k < k1;
+            a[u] = ok ? __ldcs(&vals[k]) : cmake(0.0, 0.0);           // the CB lanes of an entry read the same address (broadcast)
+            j[u] = ok ? __ldcs(&colidx[k]) : -1;                      // -1: no entry (nothing is gathered, 0 * NaN cannot occur)
+        }
+    };
+    long long k0 = 0, k1 = 0, k0n = 0, k1n = 0;
+    cplx an[SP_U]; int jn[SP_U];
+    if (row < n) { k0 = rowptr[row]; k1 = rowptr[row + 1]; }
+    load_entries(k0, k1, an, jn);
+    long long rown = row + stride;
+    if (rown < n) { k0n = rowptr[rown]; k1n = rowptr[rown + 1]; }
+    // warp-uniform trip count (a warp holds 32 / LPR lane groups): a group past its last row runs empty iterations -- its
+    // ranges are empty, so it loads and gathers nothing -- and takes part in the full-mask shuffles
+    while (__any_sync(0xffffffffu, row < n)) {
+        cplx a[SP_U]; int j[SP_U];
+#pragma unroll
+        for (int u = 0; u < SP_U; ++u) { a[u] = an[u]; j[u] = jn[u]; }
+        cplx v[SP_U];
+#pragma unroll
+        for (int u = 0; u < SP_U; ++u) v[u] = (j[u] >= 0) ? __ldg(&P[(long long)j[u] * CB + c]) : cmake(0.0, 0.0);
+        // next row of this lane group: its entries, and the rowptr pair of the row after it
+        const long long kc0 = k0, kc1 = k1, rown2 = rown + stride;
+        long long k0nn = 0, k1nn = 0;
+        load_entries(k0n, k1n, an, jn);                              // empty range (0, 0) when there is no next row
+        if (rown2 < n) { k0nn = rowptr[rown2]; k1nn = rowptr[rown2 + 1]; }
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < SP_U; ++u) cfma(acc, a[u], v[u]);
+        // rows with more than SP_LANES * SP_U entries: the remaining chunks, same order as before, not pipelined
+        for (long long kb = kc0 + SP_LANES * SP_U; kb < kc1; kb += SP_LANES * SP_U) {
+            load_entries(kb, kc1, a, j);
 #pragma unroll
             for (int u = 0; u < SP_U; ++u) v[u] = (j[u] >= 0) ? __ldg(&P[(long long)j[u] * CB + c]) : cmake(0.0, 0.0);
 #pragma unroll
             for (int u = 0; u < SP_U; ++u) cfma(acc, a[u], v[u]);
         }
-    }
 #pragma unroll
-    for (int o = SP_LANES / 2; o > 0; o >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o * CB);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o * CB);
+        for (int o = SP_LANES / 2; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o * CB);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o * CB);
+        }
+        if (sub == 0 && c < ncand && row < n) Y[(long long)(c0 + c) * ldy + row] = acc;
+        row = rown; rown = rown2; k0 = k0n; k1 = k1n; k0n = k0nn; k1n = k1nn;
     }
-    if (sub == 0 && row < n && c < ncand) Y[(long long)(c0 + c) * ldy + row] = acc;
+}
+
+// persistent-style grid for the pipelined kernel: enough CTAs for several per SM, every lane group walks many rows
+static unsigned spmm_pipe_grid(long long n, int lanes_per_row) {
+    const long long groups_per_block = SP_NT / lanes_per_row;
+    const long long need = (n + groups_per_block - 1) / groups_per_block;
+    const long long cap = (long long)MAUS_SM_COUNT_B200 * 4;          // 64 registers: four 256-thread CTAs per SM, all resident
+    return (unsigned)(need < cap ? need : cap);
 }
 
 }  // namespace
@@ -122,8 +160,7 @@ __global__ void __launch_bounds__(SP_NT) csr_spmm_packed_kernel(const long long*
 cudaError_t csr_spmm_packed4(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* P, long long p_gstride,
                              cplx* Y, long long ldy, long long n, int c0, int ctotal, int groups, cudaStream_t stream) {
     if (groups <= 0 || n <= 0) return cudaSuccess;
-    const long long threads = n * SP_LANES * 4;
-    dim3 grid((unsigned)((threads + SP_NT - 1) / SP_NT), (unsigned)groups);
+    dim3 grid(spmm_pipe_grid(n, SP_LANES * 4), (unsigned)groups);
     csr_spmm_packed_kernel<4, 3><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
     return cudaGetLastError();
 }
@@ -136,7 +173,13 @@ cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* val
     if (C <= 0) return cudaSuccess;
     // one candidate: latency bound on the dependent index -> gather chain, so occupancy beats unrolling (SP_U = 1, <= 32
     // registers, 8 CTAs / SM; measured 0.132 vs 0.140 ms at n = 1M)
-    if (C == 1) { csr_spmm_kernel<1, 1, 8><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, 0, 1); return cudaGetLastError(); }
+    if (C == 1) {
+        static int pipe1 = -1;               // MAUS_SPMM_PIPE1=0: the one-row-at-a-time kernel (A/B measurements)
+        if (pipe1 < 0) { const char* e = getenv("MAUS_SPMM_PIPE1"); pipe1 = e ? (atoi(e) != 0) : 1; }
+        if (pipe1) csr_spmm_packed_kernel<1, 3><<<dim3(spmm_pipe_grid(n, SP_LANES), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V, 0, Y, ldy, n, 0, 1);
+        else csr_spmm_kernel<1, 1, 8><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, 0, 1);
+        return cudaGetLastError();
+    }
     if (!pack_ws) {
         for (int c0 = 0; c0 < C; c0 += 4) {
             const int nc = (C - c0 < 4) ? (C - c0) : 4;
@@ -150,8 +193,7 @@ cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* val
     // (blockIdx.y = group); two candidates use the half-width layout
     if (C == 2) {
         spmm_pack_kernel<2><<<dim3(pgrid, 1), 256, 0, stream>>>(V, ldv, pack_ws, ncols, 0, C);
-        const unsigned grid2 = (unsigned)((threads * 2 + SP_NT - 1) / SP_NT);
-        csr_spmm_packed_kernel<2, 3><<<dim3(grid2, 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, 0, Y, ldy, n, 0, C);
+        csr_spmm_packed_kernel<2, 3><<<dim3(spmm_pipe_grid(n, SP_LANES * 2), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, 0, Y, ldy, n, 0, C);
         return cudaGetLastError();
     }
     const int groups = (C + 3) / 4;
