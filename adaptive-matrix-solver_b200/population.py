@@ -113,22 +113,39 @@ def _ladder(engine, ptype, v_or_x, lam, stuck, base_psi, max_attempts, pref, mat
     return None, attempts
 
 
-def _ladder_rs(rs, ptype, v_or_x, lam, stuck, alpha, base_psi, max_attempts, pref):
+def _ladder_rs(rs, ptype, v_or_x, lam, stuck, alpha, base_psi, max_attempts, pref, engine=None, M=None, b=None):
     """``_ladder`` on the row-sharded operator (every rank walks it identically: the status words are global).  A GMRES attempt
-    is ONE collective call that also mixes and takes the residual (phases solve | mix | residual); a direct-solve attempt has no
-    device counterpart for a row-sharded sparse matrix and counts as failed (AMS:57 is SuperLU, out of scope).
+    is ONE collective call that also mixes and takes the residual (phases solve | mix | residual).  A direct-solve attempt runs
+    on a REPLICATED dense copy while the order allows the batched LU (n <= LU_MAX_N: every rank factors redundantly, the matrix
+    is small); beyond that there is no device direct solver and the try counts as failed (AMS:57 is SuperLU).
     Returns (vector or None, residual, status, num_psi_attempts)."""
     fallback = 'iterative_gmres' if pref == 'direct_solve' else 'direct_solve'
     method, attempts, pending_failure = pref, 0, True
+    eigen = ptype == _abi.EIGENVALUE
     while attempts < max_attempts:
-        if not pending_failure and _METHOD.get(method) == _abi.METHOD_GMRES:
+        m = _METHOD.get(method)
+        if not pending_failure and m == _abi.METHOD_GMRES:
             psi = psi_magnitude(base_psi, attempts, stuck)
             V1 = np.ascontiguousarray(v_or_x[None, :], dtype=np.complex128).copy()
             out = rs.step(ptype, V1, [alpha], [complex(psi).real], use_jacobi=[1 if stuck > 1 else 0],
-                          sigma=[lam] if ptype == _abi.EIGENVALUE else None, phases=14)
+                          sigma=[lam] if eigen else None, phases=14)
             st = int(out["status"][0])
             if st in (_abi.ST_OK, _abi.ST_MIX_COLLAPSED):
                 return V1[0], float(out["resid"][0]), st, attempts
+        elif not pending_failure and m == _abi.METHOD_LU and engine is not None and M is not None and rs.n <= LU_MAX_N:
+            psi = psi_magnitude(base_psi, attempts, stuck)
+            cache = getattr(engine, "_matrix_cache", None)
+            if cache is None:
+                cache = engine._matrix_cache = _MatrixCache()
+            cache.ensure(engine, M, 0, 'dense')
+            if not eigen:
+                engine.set_rhs(b)
+            engine.upload_vectors(np.ascontiguousarray(v_or_x[None, :], dtype=np.complex128))
+            _, st0, _ = engine.solve_shifted([lam if eigen else 0j], [complex(psi).real], rng_key=None, method=_abi.METHOD_LU,
+                                             RHS=None, rhs_shared=not eigen, want_x=False)
+            if int(st0[0]) == _abi.ST_OK:
+                Vn, r1, _, st1 = engine.mix_residual(ptype, [alpha], [lam])
+                return Vn[0], float(r1[0]), int(st1[0]), attempts
         pending_failure = False
         if method == pref and pref != fallback and attempts == 0:          # AMS:99-102
             method = fallback
@@ -193,7 +210,8 @@ def step_population(candidates, M, b, strat_params, problem_knowledge, engine, c
         for c in gpu:
             c.b_vector = b                                                                     # AMS:146
             c.prev_residual = c.residual_k                                                     # AMS:147
-        _step_group(gpu, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, _abi.SLOT_CURRENT, rs)
+        _step_group(gpu, ptype, N, b, engine, State, base_psi, max_retries, pref, is_sparse, conv_tol, _abi.SLOT_CURRENT, rs,
+                    M_cur=M)
         return len(gpu)
     if pref == 'direct_solve' and m_sparse and N <= LU_MAX_N:
         form = 'dense'
@@ -270,7 +288,7 @@ def _step_group(cands, ptype, N, b, engine, State, base_psi, max_retries, pref, 
         need_residual = False
         if st in (_abi.ST_ZERO_PIVOT, _abi.ST_NONFINITE, _abi.ST_GMRES_NOCONV) and rs is not None:
             vec, r1, st1, retries = _ladder_rs(rs, ptype, V_before[i], complex(lam[i]), int(stuck[i]), float(alpha[i]), base_psi,
-                                               max_retries, pref)
+                                               max_retries, pref, engine, M_cur, b)
             if vec is not None:
                 V[i] = vec
                 resid[i] = r1

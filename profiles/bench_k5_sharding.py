@@ -85,7 +85,7 @@ for _ in range(5):
     op.matvec(Rloc)
 p = eng.profile_read(); eng.profile_reset(False)
 if rank == 0:
-    print(json.dumps(dict(mode="row-sharded matrix (all-gather per SpMM, all-reduce per dot)", n=n, n_gpus=world,
+    print(json.dumps(dict(mode=op.mode_description(), n=n, n_gpus=world,
                           candidates_total=Call, seconds=round(dt_b, 4), candidate_solves_per_s=round(Call / dt_b, 1),
                           inner_iters=it.tolist()[:8], status=st.tolist()[:8], rel_residual_c0=rel_b,
                           spmm_ms_all_candidates=round(p["matvec_ms"] / max(1, p["matvec_launches"]), 3),
