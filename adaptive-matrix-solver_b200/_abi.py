@@ -18,7 +18,7 @@ EXPORTS = [
     "maus_free_pinned", "maus_set_dense", "maus_add_dense_form", "maus_set_csc", "maus_set_rhs", "maus_upload_vectors",
     "maus_download_vectors", "maus_download_vector_range", "maus_rq", "maus_solve_shifted", "maus_solve_with_R", "maus_mix_residual",
     "maus_residual", "maus_step", "maus_launch_count", "maus_profile_reset", "maus_profile_read", "maus_profile_read_kind", "maus_stream", "maus_debug_zgemm", "maus_svd_set_matrix", "maus_svd_step", "maus_svd_residual",
-    "maus_gram", "maus_project", "maus_diag_dense", "maus_cond2_estimate", "maus_nccl_unique_id", "maus_dist_init", "maus_dist_info", "maus_gather", "maus_set_csr_rowblock",
+    "maus_gram", "maus_project", "maus_heev", "maus_diag_dense", "maus_cond2_estimate", "maus_nccl_unique_id", "maus_dist_init", "maus_dist_info", "maus_gather", "maus_set_csr_rowblock",
     "maus_rs_set_rhs", "maus_rs_matvec", "maus_rs_gmres", "maus_rs_step",
 ]
 
@@ -88,6 +88,7 @@ def load_library():
         "maus_svd_residual": (i32, [vp, i64, dp, dp, dp, dp]),
         "maus_gram": (i32, [vp, i64, i64, dp, dp]),
         "maus_project": (i32, [vp, i64, i64, dp, i64, dp, dp]),
+        "maus_heev": (i32, [vp, i64, dp, i32, dp, dp, i32p, dp]),
         "maus_diag_dense": (i32, [vp, C.c_double, C.c_double, i64p, i32p, i32p]),
         "maus_cond2_estimate": (i32, [vp, i32, i32, dp, dp, dp, i32p]),
         "maus_nccl_unique_id": (i32, [C.c_char_p, C.c_char_p]),

@@ -70,6 +70,8 @@ struct maus_ctx {
     void* svd = nullptr;
     // row-sharded sparse operator + NCCL communicator (rowshard.cu)
     void* rowshard = nullptr;
+    // Hermitian eigensolver workspace (heev.cu)
+    void* heev = nullptr;
 
     long long launches = 0;
     long long bytes_held = 0;
@@ -114,3 +116,4 @@ int maus_gmres_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double
 void maus_gmres_free(maus_ctx* ctx);
 void maus_svd_free(maus_ctx* ctx);
 void maus_rowshard_free(maus_ctx* ctx);
+void maus_heev_free(maus_ctx* ctx);

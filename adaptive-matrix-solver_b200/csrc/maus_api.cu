@@ -208,6 +208,7 @@ extern "C" int maus_destroy(maus_ctx* ctx) {
     reset_for_n(ctx, 0);
     maus_svd_free(ctx);
     maus_rowshard_free(ctx);
+    maus_heev_free(ctx);
     for (auto& e : ctx->prof.ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -582,11 +582,9 @@ static void gemv_launch(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y,
 cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
                               cudaStream_t stream) {
     // grid sized so that several waves of CTAs cover the 148 SMs: 8 rows per CTA below n = 8192, 16 above
-    static int rpw4 = -1;                    // MAUS_GEMV_RPW4=0/1/2: A/B switch of the four-rows-per-warp shapes for several candidates
-    if (rpw4 < 0) { const char* e = getenv("MAUS_GEMV_RPW4"); rpw4 = e ? atoi(e) : 0; }
-    if (C >= 2 && n >= 2048 && rpw4 == 1) gemv_launch<4, 64>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
-    else if (C >= 2 && n >= 2048 && rpw4 == 2) gemv_launch<4, 128>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
-    else if (n >= 8192) gemv_launch<2, 256>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
+    // (four rows per warp were measured in round 2: 0.32 / 0.47 of the HBM peak at n = 4096 against 0.61 -- register pressure
+    // costs more occupancy than the halved shared-memory traffic returns)
+    if (n >= 8192) gemv_launch<2, 256>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
     else if (C >= 2 && n >= 2048) gemv_launch<2, 128>(A_rm, V, ldv, Y, ldy, n, n, C, stream);   // several candidates: LDS-bound at RPW = 1
     else gemv_launch<1, 256>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
     return cudaGetLastError();

