@@ -29,3 +29,27 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:58s} {v[0]:8d} {v[1]:10.3f} {v[1] / tot * 100:6.1f}% {v[1] / v[0] * 1e3:10.1f}"
           + (f" {v[2] / 1e9:11.3f} {v[3] / 1e9:11.3f}" if has_dram else ''))
 print(f"{'total':58s} {sum(v[0] for v in agg.values()):8d} {tot:10.3f}")
+
+# optional:  python profiles/summarize_launches.py file.csv --traffic-json profiles/ncu_traffic.json --candidates 16 [--source name]
+# writes the DRAM traffic record bench.py's roofline.traffic is computed from (stamped with the kernel sources' sha)
+if "--traffic-json" in sys.argv and has_dram:
+    import hashlib, json, os, subprocess
+    out = sys.argv[sys.argv.index("--traffic-json") + 1]
+    cand = int(sys.argv[sys.argv.index("--candidates") + 1])
+    src = sys.argv[sys.argv.index("--source") + 1] if "--source" in sys.argv else sys.argv[1]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha256()
+    for f in ("zgemm.cu", "zgemm.cuh", "lu.cu", "lu.cuh"):
+        h.update(open(os.path.join(root, "adaptive-matrix-solver_b200", "csrc", f), "rb").read())
+    gemm = [v for k, v in agg.items() if k.startswith("zgemm3m")]
+    rd = sum(v[2] for v in gemm); wr = sum(v[3] for v in gemm); n_l = sum(v[0] for v in gemm)
+    try:
+        commit = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    except Exception:
+        commit = None
+    json.dump({"source": src, "commit": commit, "candidates_measured": cand, "gemm_launches": n_l,
+               "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes_per_candidate": (rd + wr) / cand,
+               "kernel_sources_sha16": h.hexdigest()[:16],
+               "note": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the zgemm3m_dmma_kernel launches of ONE generation"},
+              open(out, "w"), indent=1)
+    print(f"wrote {out}: {(rd + wr) / cand / 1e9:.3f} GB per candidate over {n_l} GEMM launches")
