@@ -83,8 +83,11 @@ __global__ void __launch_bounds__(256) spmm_pack_kernel(const cplx* __restrict__
 // at a time the kernel was bound by that latency (ncu, round 2: DRAM 31 %, L2 31 %, l1tex 58 % busy at 63 % occupancy).  The
 // lane groups therefore walk their rows grid-strided and SOFTWARE-PIPELINED: while the gathers of row r are in flight, the
 // (index, value) loads of the group's next row and the rowptr pair of the row after that are already issued.
-template <int CB, int SP_U, int PD>
-__global__ void __launch_bounds__(SP_NT) csr_spmm_packed_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+// MINB = CTAs per SM the register allocation is held to (the kernel is bound by the latency of its dependent loads: warps in
+// flight matter more than look-ahead depth -- two rows of look-ahead at 114 registers measured 0.48 ms, one row at 64 registers
+// 0.29 ms for 4 candidates at n = 1M)
+template <int CB, int SP_U, int MINB>
+__global__ void __launch_bounds__(SP_NT, MINB) csr_spmm_packed_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx,
                                                                 const cplx* __restrict__ vals, const cplx* __restrict__ P,
                                                                 long long p_gstride, cplx* __restrict__ Y, long long ldy,
                                                                 long long n, int c0, int ctotal) {
@@ -106,43 +109,26 @@ __global__ void __launch_bounds__(SP_NT) csr_spmm_packed_kernel(const long long*
             j[u] = ok ? __ldcs(&colidx[k]) : -1;                      // -1: no entry (nothing is gathered, 0 * NaN cannot occur)
         }
     };
-    // pipeline state: slot 0 = the row being multiplied, slots 1 .. PD = the next rows of this lane group whose (index, value)
-    // loads are in flight, kr[PD + 1] = the rowptr pair of the row after those (PD = rows of look-ahead: the matrix stream comes
-    // from HBM, one row of look-ahead does not cover its latency under load)
-    long long kr0[PD + 2], kr1[PD + 2];
-    cplx ap[PD + 1][SP_U]; int jp[PD + 1][SP_U];
-#pragma unroll
-    for (int d = 0; d <= PD + 1; ++d) {
-        const long long r = row + d * stride;
-        kr0[d] = 0; kr1[d] = 0;
-        if (r < n) { kr0[d] = rowptr[r]; kr1[d] = rowptr[r + 1]; }
-    }
-#pragma unroll
-    for (int d = 0; d <= PD; ++d) load_entries(kr0[d], kr1[d], ap[d], jp[d]);
+    long long k0 = 0, k1 = 0, k0n = 0, k1n = 0;
+    cplx an[SP_U]; int jn[SP_U];
+    if (row < n) { k0 = rowptr[row]; k1 = rowptr[row + 1]; }
+    load_entries(k0, k1, an, jn);
+    long long rown = row + stride;
+    if (rown < n) { k0n = rowptr[rown]; k1n = rowptr[rown + 1]; }
     // warp-uniform trip count (a warp holds 32 / LPR lane groups): a group past its last row runs empty iterations -- its
     // ranges are empty, so it loads and gathers nothing -- and takes part in the full-mask shuffles
     while (__any_sync(0xffffffffu, row < n)) {
         cplx a[SP_U]; int j[SP_U];
 #pragma unroll
-        for (int u = 0; u < SP_U; ++u) { a[u] = ap[0][u]; j[u] = jp[0][u]; }
+        for (int u = 0; u < SP_U; ++u) { a[u] = an[u]; j[u] = jn[u]; }
         cplx v[SP_U];
 #pragma unroll
         for (int u = 0; u < SP_U; ++u) v[u] = (j[u] >= 0) ? __ldg(&P[(long long)j[u] * CB + c]) : cmake(0.0, 0.0);
-        const long long kc0 = kr0[0], kc1 = kr1[0];
-        // shift the pipeline: rows 1 .. PD move up, the entries of row PD + 1 and the rowptr pair of row PD + 2 are issued
-#pragma unroll
-        for (int d = 0; d < PD; ++d) {
-#pragma unroll
-            for (int u = 0; u < SP_U; ++u) { ap[d][u] = ap[d + 1][u]; jp[d][u] = jp[d + 1][u]; }
-        }
-#pragma unroll
-        for (int d = 0; d <= PD; ++d) { kr0[d] = kr0[d + 1]; kr1[d] = kr1[d + 1]; }
-        load_entries(kr0[PD], kr1[PD], ap[PD], jp[PD]);              // empty range (0, 0) when there is no such row
-        {
-            const long long r = row + (long long)(PD + 2) * stride;
-            kr0[PD + 1] = 0; kr1[PD + 1] = 0;
-            if (r < n) { kr0[PD + 1] = rowptr[r]; kr1[PD + 1] = rowptr[r + 1]; }
-        }
+        // next row of this lane group: its entries, and the rowptr pair of the row after it
+        const long long kc0 = k0, kc1 = k1, rown2 = rown + stride;
+        long long k0nn = 0, k1nn = 0;
+        load_entries(k0n, k1n, an, jn);                              // empty range (0, 0) when there is no next row
+        if (rown2 < n) { k0nn = rowptr[rown2]; k1nn = rowptr[rown2 + 1]; }
         cplx acc = cmake(0.0, 0.0);
 #pragma unroll
         for (int u = 0; u < SP_U; ++u) cfma(acc, a[u], v[u]);
@@ -160,17 +146,17 @@ __global__ void __launch_bounds__(SP_NT) csr_spmm_packed_kernel(const long long*
             acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o * CB);
         }
         if (sub == 0 && c < ncand && row < n) Y[(long long)(c0 + c) * ldy + row] = acc;
-        row += stride;
+        row = rown; rown = rown2; k0 = k0n; k1 = k1n; k0n = k0nn; k1n = k1nn;
     }
 }
 
 // persistent-style grid for the pipelined kernel: exactly the CTAs that are resident at once (occupancy query per instantiation),
 // every lane group walks many rows
-template <int CB, int SP_U, int PD>
+template <int CB, int SP_U, int MINB>
 static unsigned spmm_pipe_grid(long long n) {
     static int per_sm = 0;
     if (!per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_packed_kernel<CB, SP_U, PD>, SP_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_packed_kernel<CB, SP_U, MINB>, SP_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
     }
     const long long groups_per_block = SP_NT / (SP_LANES * CB);
     const long long need = (n + groups_per_block - 1) / groups_per_block;
@@ -183,10 +169,11 @@ static unsigned spmm_pipe_grid(long long n) {
 cudaError_t csr_spmm_packed4(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* P, long long p_gstride,
                              cplx* Y, long long ldy, long long n, int c0, int ctotal, int groups, cudaStream_t stream) {
     if (groups <= 0 || n <= 0) return cudaSuccess;
-    static int pd = -1;                      // MAUS_SPMM_PD=1: one row of look-ahead (A/B measurements)
-    if (pd < 0) { const char* e = getenv("MAUS_SPMM_PD"); pd = e ? atoi(e) : 2; }
-    if (pd == 1) csr_spmm_packed_kernel<4, 3, 1><<<dim3(spmm_pipe_grid<4, 3, 1>(n), (unsigned)groups), SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
-    else csr_spmm_packed_kernel<4, 3, 2><<<dim3(spmm_pipe_grid<4, 3, 2>(n), (unsigned)groups), SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
+    static int minb = -1;                    // MAUS_SPMM_MINB=5 / 6: hold the kernel to 51 / 42 registers (A/B measurements)
+    if (minb < 0) { const char* e = getenv("MAUS_SPMM_MINB"); minb = e ? atoi(e) : 4; }
+    if (minb == 5) csr_spmm_packed_kernel<4, 3, 5><<<dim3(spmm_pipe_grid<4, 3, 5>(n), (unsigned)groups), SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
+    else if (minb == 6) csr_spmm_packed_kernel<4, 3, 6><<<dim3(spmm_pipe_grid<4, 3, 6>(n), (unsigned)groups), SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
+    else csr_spmm_packed_kernel<4, 3, 4><<<dim3(spmm_pipe_grid<4, 3, 4>(n), (unsigned)groups), SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
     return cudaGetLastError();
 }
 
@@ -201,7 +188,7 @@ cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* val
     if (C == 1) {
         static int pipe1 = -1;               // MAUS_SPMM_PIPE1=0: the one-row-at-a-time kernel (A/B measurements)
         if (pipe1 < 0) { const char* e = getenv("MAUS_SPMM_PIPE1"); pipe1 = e ? (atoi(e) != 0) : 1; }
-        if (pipe1) csr_spmm_packed_kernel<1, 3, 2><<<dim3(spmm_pipe_grid<1, 3, 2>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V, 0, Y, ldy, n, 0, 1);
+        if (pipe1) csr_spmm_packed_kernel<1, 3, 4><<<dim3(spmm_pipe_grid<1, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V, 0, Y, ldy, n, 0, 1);
         else csr_spmm_kernel<1, 1, 8><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, 0, 1);
         return cudaGetLastError();
     }
@@ -218,7 +205,7 @@ cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* val
     // (blockIdx.y = group); two candidates use the half-width layout
     if (C == 2) {
         spmm_pack_kernel<2><<<dim3(pgrid, 1), 256, 0, stream>>>(V, ldv, pack_ws, ncols, 0, C);
-        csr_spmm_packed_kernel<2, 3, 2><<<dim3(spmm_pipe_grid<2, 3, 2>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, 0, Y, ldy, n, 0, C);
+        csr_spmm_packed_kernel<2, 3, 4><<<dim3(spmm_pipe_grid<2, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, 0, Y, ldy, n, 0, C);
         return cudaGetLastError();
     }
     const int groups = (C + 3) / 4;
