@@ -256,12 +256,13 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    shard = Shard(rank, world, dev if world > 1 else None)
-
     n, C_ = args.n, args.candidates
     A = k2_matrix(n, seed=20260)
     V0 = initial_vectors(C_, n, seed=20260 + 1000 * rank)
     eng = pkg.MausEngine(local)
+    if world > 1:
+        eng.enable_row_sharding(rank, world)      # NCCL communicator of the context: maus_gather + the row-sharded operator
+    shard = Shard(rank, world, dev if world > 1 else None, engine=eng if world > 1 else None)
     eng.set_matrix(A)
     stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
     base_psi = PSI_EPSILON_BASE * 1.0
@@ -315,6 +316,22 @@ def run_b200(args):
     e2e_s = shard.all_reduce_max(time.perf_counter() - t0)
     e2e_value = world * C_ * e2e_steps / e2e_s
     vec_bytes = C_ * n * 16
+    replicas = None
+    if world > 1:
+        # multi-rank parity observed by the driver: after the sharded generations every rank must hold the SAME population
+        # (bit for bit: each candidate is computed by exactly one rank and all-gathered), and rank 0's copy of a candidate that
+        # ANOTHER rank stepped must satisfy the step's invariants (unit norm, residual consistent with a host recomputation)
+        import hashlib
+        h = hashlib.sha256()
+        for c in cands:
+            h.update(np.ascontiguousarray(c.v_k).tobytes()); h.update(np.complex128(c.lambda_k).tobytes())
+            h.update(np.float64(c.residual_k).tobytes())
+        dig = float(int.from_bytes(h.digest()[:6], "little"))
+        same = shard.all_reduce_max(dig) == -shard.all_reduce_max(-dig)
+        other = cands[(rank + 1) % world]                      # owned by the next rank (live candidate i -> rank i mod G)
+        r_host = float(np.linalg.norm(A @ other.v_k - other.lambda_k * other.v_k))
+        replicas = {"identical_on_all_ranks": bool(same), "foreign_candidate_unit_norm_err": abs(float(np.linalg.norm(other.v_k)) - 1.0),
+                    "foreign_candidate_residual": float(other.residual_k), "foreign_candidate_residual_recomputed": r_host}
     del cands
 
     # ------------------------------------------------------------------ roofline of the dominant kernel
@@ -380,7 +397,8 @@ def run_b200(args):
                         "api": ("step_population(candidates, M, b, strat_params, problem_knowledge, engine)" if world == 1 else
                                 "step_population_sharded(candidates, M, b, strat_params, problem_knowledge, engine, shard): "
                                 "per-generation all-gather of record + vector of every candidate inside the timed region"),
-                        "allgather_bytes_per_rank_per_step": 0 if world == 1 else C_ * (14 + 2 * n) * 8},
+                        "allgather_bytes_per_rank_per_step": 0 if world == 1 else C_ * (14 + 2 * n) * 8,
+                        "sharded_replicas": replicas},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "step_breakdown_ms": {k: round(v["ms"] / args.steps, 2) for k, v in breakdown.items() if v["launches"]},
                 "wall_s_timed": round(wall, 3), "min_residual": float(np.min(out["resid"])),
@@ -591,7 +609,6 @@ def bench_k5(pkg, eng, stream, torch, _abi, n=1_000_000, C_=8):
 def bench_k5_rowshard(pkg, eng, shard, torch, _abi, rank, world, n=1_000_000, C_per_gpu=8):
     """BASELINE config 5 as worded: the matrix ROW-SHARDED over the N GPUs (rank r owns n / N rows and that slice of every vector),
     N x 8 linear solves done jointly; beside it the default mode (matrix replicated, 8 solves per GPU) on the same box."""
-    from adaptive_matrix_solver_b200.rowshard import RowShardedOperator
     from adaptive_matrix_solver_b200.workloads import k5_sparse
     A = k5_sparse(n)
     psi = np.full(C_per_gpu, 5e-19); zero = np.zeros(C_per_gpu, dtype=complex)
@@ -602,7 +619,7 @@ def bench_k5_rowshard(pkg, eng, shard, torch, _abi, rank, world, n=1_000_000, C_
     shard.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
     _, st_a, it_a = eng.solve_shifted(zero, psi, rng_key=None, method=_abi.METHOD_GMRES, RHS=RHS, want_x=False)
     dt_a = shard.all_reduce_max(time.perf_counter() - t0)
-    op = RowShardedOperator(eng, rank, world)
+    op = eng.enable_row_sharding(rank, world)
     op.set_matrix(A)
     Call = C_per_gpu * world
     rng = np.random.default_rng(100)
