@@ -149,7 +149,7 @@ int maus_ensure_population(maus_ctx* ctx, long long C) {
 
 static void free_slot(maus_ctx* ctx, MatrixSlot& s, long long n) {
     maus_dev_free(ctx, s.rm, n * n * sizeof(cplx)); maus_dev_free(ctx, s.cm, n * n * sizeof(cplx));
-    maus_dev_free(ctx, s.rowptr, (n + 1) * 8); maus_dev_free(ctx, s.colidx, s.nnz * 4);
+    maus_dev_free(ctx, s.rowptr, (n + 1) * 8); maus_dev_free(ctx, s.colidx, s.nnz * 4 + 16);
     maus_dev_free(ctx, s.vals, s.nnz * sizeof(cplx)); maus_dev_free(ctx, s.diag, n * sizeof(cplx));
     if (s.pack) maus_dev_free(ctx, s.pack, s.pack_elems * sizeof(cplx));
     s = MatrixSlot();
@@ -361,7 +361,7 @@ extern "C" int maus_set_csc(maus_ctx* ctx, int slot, int64_t n, int64_t nnz, con
         }
     }
     MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.rowptr, (size_t)(n + 1) * 8));
-    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.colidx, (size_t)nnz * 4));
+    MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.colidx, (size_t)nnz * 4 + 16));   // + 16: the staged SpMM copies whole 16-byte units
     MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.vals, (size_t)nnz * sizeof(cplx)));
     MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.diag, (size_t)n * sizeof(cplx)));
     s.nnz = nnz;

@@ -430,7 +430,7 @@ extern "C" int maus_set_csr_rowblock(maus_ctx* ctx, int64_t n, int64_t row0, int
     cudaFree(rs->rowptr); cudaFree(rs->colidx); cudaFree(rs->vals); cudaFree(rs->diag);
     rs->rowptr = nullptr; rs->colidx = nullptr; rs->vals = nullptr; rs->diag = nullptr;
     MAUS_CUDA(ctx, cudaMalloc(&rs->rowptr, (size_t)(nrows + 1) * 8));
-    MAUS_CUDA(ctx, cudaMalloc(&rs->colidx, std::max<size_t>((size_t)nnz * 4, 16)));
+    MAUS_CUDA(ctx, cudaMalloc(&rs->colidx, (size_t)nnz * 4 + 16));          // + 16: the staged SpMM copies whole 16-byte units
     MAUS_CUDA(ctx, cudaMalloc(&rs->vals, std::max<size_t>((size_t)nnz * sizeof(cplx), 16)));
     MAUS_CUDA(ctx, cudaMalloc(&rs->diag, (size_t)nrows * sizeof(cplx)));
     MAUS_CUDA(ctx, cudaMemcpy(rs->rowptr, rp.data(), (size_t)(nrows + 1) * 8, cudaMemcpyHostToDevice));
