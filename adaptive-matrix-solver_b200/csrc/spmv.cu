@@ -336,25 +336,71 @@ static unsigned spmm_pipe_grid(long long n) {
 
 }  // namespace
 
+// L2 residency of the interleaved copy.  The gathers hit P at random; one group of P at n = 1M is 64 MB, the matrix streams
+// 440 MB through the same L2 and (ncu, round 2) ~30 % of the gathered sectors missed and became random DRAM reads.  With
+// MAUS_SPMM_L2PERSIST (fraction of P marked persisting, e.g. 0.6) the groups are launched one by one, each with an access-policy
+// window over its own copy: persisting for P, streaming for everything else.
+static float spmm_l2_persist_ratio() {
+    static float ratio = -1.f;
+    if (ratio < 0.f) {
+        const char* e = getenv("MAUS_SPMM_L2PERSIST");
+        ratio = e ? (float)atof(e) : 0.f;
+        if (ratio > 0.f) {
+            int dev = 0; cudaGetDevice(&dev);
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0 ||
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) != cudaSuccess) {
+                cudaGetLastError(); ratio = 0.f;
+            }
+        }
+    }
+    return ratio;
+}
+
+template <class Launch>
+static cudaError_t spmm_launch_groups(const cplx* P, long long p_gstride, int groups, cudaStream_t stream, Launch launch) {
+    const float ratio = spmm_l2_persist_ratio();
+    if (ratio <= 0.f || p_gstride <= 0) { launch(0, groups); return cudaGetLastError(); }
+    int dev = 0; cudaGetDevice(&dev);
+    int max_win = 0; cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    for (int g = 0; g < groups; ++g) {
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.base_ptr = const_cast<cplx*>(P + (long long)g * p_gstride);
+        size_t bytes = (size_t)p_gstride * sizeof(cplx);
+        if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = ratio > 1.f ? 1.f : ratio;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        launch(g, 1);
+    }
+    cudaStreamAttrValue off = {};
+    off.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &off);
+    return cudaGetLastError();
+}
+
 cudaError_t csr_spmm_packed4(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* P, long long p_gstride,
                              cplx* Y, long long ldy, long long n, int c0, int ctotal, int groups, cudaStream_t stream) {
     if (groups <= 0 || n <= 0) return cudaSuccess;
-    static int staged = -1;                  // MAUS_SPMM_STAGED=0: the register-pipelined kernel (A/B measurements)
-    if (staged < 0) { const char* e = getenv("MAUS_SPMM_STAGED"); staged = e ? atoi(e) : 1; }
+    static int staged = -1;                  // MAUS_SPMM_STAGED=1: the shared-memory staged kernel (measured slower: 0.37 vs 0.33 ms)
+    if (staged < 0) { const char* e = getenv("MAUS_SPMM_STAGED"); staged = e ? atoi(e) : 0; }
     if (staged) {
         static int per_sm = 0;
         if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_staged_kernel<4, 4>, ST_NT, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
         const long long nblocks = (n + ST_RB - 1) / ST_RB, cap = (long long)MAUS_SM_COUNT_B200 * per_sm;
-        dim3 grid((unsigned)(nblocks < cap ? nblocks : cap), (unsigned)groups);
-        csr_spmm_staged_kernel<4, 4><<<grid, ST_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
-        return cudaGetLastError();
+        const unsigned gx = (unsigned)(nblocks < cap ? nblocks : cap);
+        return spmm_launch_groups(P, p_gstride, groups, stream, [&](int g0, int ng) {
+            csr_spmm_staged_kernel<4, 4><<<dim3(gx, (unsigned)ng), ST_NT, 0, stream>>>(rowptr, colidx, vals, P + (long long)g0 * p_gstride, p_gstride,
+                                                                                    Y, ldy, n, c0 + 4 * g0, ctotal);
+        });
     }
-    static int minb = -1;                    // MAUS_SPMM_MINB=5 / 6: hold the kernel to 51 / 42 registers (A/B measurements)
-    if (minb < 0) { const char* e = getenv("MAUS_SPMM_MINB"); minb = e ? atoi(e) : 4; }
-    if (minb == 5) csr_spmm_packed_kernel<4, 3, 5><<<dim3(spmm_pipe_grid<4, 3, 5>(n), (unsigned)groups), SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
-    else if (minb == 6) csr_spmm_packed_kernel<4, 3, 6><<<dim3(spmm_pipe_grid<4, 3, 6>(n), (unsigned)groups), SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
-    else csr_spmm_packed_kernel<4, 3, 4><<<dim3(spmm_pipe_grid<4, 3, 4>(n), (unsigned)groups), SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
-    return cudaGetLastError();
+    const unsigned gx = spmm_pipe_grid<4, 3, 4>(n);
+    return spmm_launch_groups(P, p_gstride, groups, stream, [&](int g0, int ng) {
+        csr_spmm_packed_kernel<4, 3, 4><<<dim3(gx, (unsigned)ng), SP_NT, 0, stream>>>(rowptr, colidx, vals, P + (long long)g0 * p_gstride, p_gstride,
+                                                                                    Y, ldy, n, c0 + 4 * g0, ctotal);
+    });
 }
 
 cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* V, long long ldv, cplx* Y,
