@@ -1,7 +1,6 @@
 // spmv.cu -- CSR sparse matrix x candidate block (SpMM) for the sparse GMRES path (AMS:47, 57 replaced by GMRES;
 // the reference's matrix is scipy CSC, converted once to CSR at upload so that rows are contiguous).
 #include <cstdlib>
-#include <cstdint>
 #include "spmv.cuh"
 
 namespace {
@@ -151,175 +150,6 @@ __global__ void __launch_bounds__(SP_NT, MINB) csr_spmm_packed_kernel(const long
     }
 }
 
-// ---- staged variant: the matrix stream goes through SHARED memory -------------------------------------------------------------
-// In the kernel above every in-flight row holds its (value, index) pairs in registers -- four times over, once per candidate
-// lane -- which caps the warps per SM at 32 and with them the gathers in flight.  Here a CTA walks blocks of ST_RB rows; the
-// contiguous value / index ranges of a block are fetched by two bulk async copies (TMA, no registers, two stages deep), the
-// lanes read them with LDS and only the gathers remain as exposed global round trips: ~45 registers, five CTAs per SM, six
-// gathers in flight per lane.  Blocks with more than ST_CAP entries (rows far longer than the K5 family's ~21) take the same
-// arithmetic from global memory.  Per-candidate summation order unchanged (bit-identical to the other kernels).
-constexpr int ST_RB = 32, ST_CAP = 1024, ST_NT = 256;
-struct __align__(16) SpmmStage {
-    cplx vals[ST_CAP];
-    int idx[ST_CAP + 8];
-    long long rp[ST_RB + 1];
-    int direct, pad;
-};
-__device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void sp_mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void sp_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sp_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void sp_mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(sp_smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void sp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(sp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sp_smem_u32(bar)) : "memory");
-}
-
-template <int CB, int MINB>
-__global__ void __launch_bounds__(ST_NT, MINB) csr_spmm_staged_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx,
-                                                                      const cplx* __restrict__ vals, const cplx* __restrict__ P,
-                                                                      long long p_gstride, cplx* __restrict__ Y, long long ldy,
-                                                                      long long n, int c0, int ctotal) {
-    constexpr int LPR = SP_LANES * CB;                     // lanes per row
-    constexpr int RPW = 32 / LPR;                          // rows a warp works on at the same time
-    constexpr int NW = ST_NT / 32;
-    static_assert(ST_RB % (NW * RPW) == 0, "rows of a block must split evenly over the warps");
-    __shared__ SpmmStage st[2];
-    __shared__ __align__(8) uint64_t bar[2];
-    P += (long long)blockIdx.y * p_gstride;                // blockIdx.y = group of CB candidates
-    c0 += (int)blockIdx.y * CB;
-    const int ncand = min(CB, ctotal - c0);
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int l = lane % LPR, sub = l / CB, c = l % CB, rsel = lane / LPR;
-    const long long nblocks = (n + ST_RB - 1) / ST_RB;
-    if (t == 0) { sp_mbar_init(&bar[0], 1); sp_mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncthreads();
-    // warp 0 stages block b into stage s: the rowptr slice (already in its registers), then the two bulk copies
-    auto issue = [&](long long b, int s, long long rp_lane, long long rp_last) {
-        if (b >= nblocks) return;
-        const long long r0 = b * ST_RB;
-        const int nr = (int)min((long long)ST_RB, n - r0);
-        if (lane <= nr) st[s].rp[lane] = rp_lane;
-        if (lane == 0 && nr == ST_RB) st[s].rp[ST_RB] = rp_last;
-        __syncwarp();
-        if (lane == 0) {
-            const long long k0 = st[s].rp[0], k1 = st[s].rp[nr];
-            const long long ks = k0 & ~3LL;                                  // index copy starts 16-byte aligned
-            const long long E = k1 - k0;
-            const bool direct = E > ST_CAP;
-            st[s].direct = direct ? 1 : 0;
-            uint32_t bv = 0, bi = 0;
-            if (!direct && E > 0) { bv = (uint32_t)(E * sizeof(cplx)); bi = (uint32_t)(((k1 - ks + 3) & ~3LL) * sizeof(int)); }
-            sp_mbar_expect_tx(&bar[s], bv + bi);
-            if (bv) { sp_bulk_g2s(st[s].vals, vals + k0, bv, &bar[s]); sp_bulk_g2s(st[s].idx, colidx + ks, bi, &bar[s]); }
-        }
-    };
-    auto load_rp = [&](long long b, long long& rp_lane, long long& rp_last) {
-        rp_lane = 0; rp_last = 0;
-        if (b >= nblocks) return;
-        const long long r0 = b * ST_RB;
-        const int nr = (int)min((long long)ST_RB, n - r0);
-        if (lane <= nr) rp_lane = rowptr[r0 + lane];
-        if (lane == 0 && nr == ST_RB) rp_last = rowptr[r0 + ST_RB];
-    };
-    long long b = blockIdx.x;
-    if (warp == 0) {
-        long long a0, a1;
-        load_rp(b, a0, a1); issue(b, 0, a0, a1);
-        load_rp(b + gridDim.x, a0, a1); issue(b + gridDim.x, 1, a0, a1);
-    }
-    uint32_t phase[2] = {0, 0};
-    for (int s = 0; b < nblocks; b += gridDim.x, s ^= 1) {
-        long long nx0 = 0, nx1 = 0;
-        if (warp == 0) load_rp(b + 2LL * gridDim.x, nx0, nx1);               // in flight behind this block's gathers
-        sp_mbar_wait(&bar[s], phase[s]); phase[s] ^= 1;
-        const SpmmStage& S = st[s];
-        const long long r0 = b * ST_RB;
-        const long long kbase = S.rp[0], ibase = kbase & ~3LL;
-        const bool direct = S.direct != 0;
-        // each warp: rows (warp * RPW + rsel) + i * NW * RPW of the block, two at a time -> 2 * 3 gathers in flight per lane
-#pragma unroll 1
-        for (int i = 0; i < ST_RB / (NW * RPW); i += 2) {
-            cplx acc[2]; long long ra[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                acc[h] = cmake(0.0, 0.0);
-                const int lr = warp * RPW + rsel + (i + h) * NW * RPW;
-                ra[h] = (i + h < ST_RB / (NW * RPW)) ? r0 + lr : n;
-            }
-            long long k0r[2], k1r[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const bool live = ra[h] < n;
-                k0r[h] = live ? S.rp[ra[h] - r0] : 0;
-                k1r[h] = live ? S.rp[ra[h] - r0 + 1] : 0;
-            }
-            // first chunk of both rows: indices -> gathers issued together, then values and FMAs
-            int j[2][3]; cplx v[2][3];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const long long k = k0r[h] + sub + u * SP_LANES;
-                    j[h][u] = (k < k1r[h]) ? (direct ? __ldcs(&colidx[k]) : S.idx[k - ibase]) : -1;
-                }
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int u = 0; u < 3; ++u) v[h][u] = (j[h][u] >= 0) ? __ldg(&P[(long long)j[h][u] * CB + c]) : cmake(0.0, 0.0);
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const long long k = k0r[h] + sub + u * SP_LANES;
-                    if (j[h][u] >= 0) cfma(acc[h], direct ? __ldcs(&vals[k]) : S.vals[k - kbase], v[h][u]);
-                    else cfma(acc[h], cmake(0.0, 0.0), v[h][u]);             // same operation sequence as the register kernels
-                }
-            // rows longer than 24 entries: remaining chunks, same order
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                for (long long kb = k0r[h] + SP_LANES * 3; kb < k1r[h]; kb += SP_LANES * 3) {
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const long long k = kb + sub + u * SP_LANES;
-                        j[h][u] = (k < k1r[h]) ? (direct ? __ldcs(&colidx[k]) : S.idx[k - ibase]) : -1;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) v[h][u] = (j[h][u] >= 0) ? __ldg(&P[(long long)j[h][u] * CB + c]) : cmake(0.0, 0.0);
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const long long k = kb + sub + u * SP_LANES;
-                        cfma(acc[h], (j[h][u] >= 0) ? (direct ? __ldcs(&vals[k]) : S.vals[k - kbase]) : cmake(0.0, 0.0), v[h][u]);
-                    }
-                }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int o = SP_LANES / 2; o > 0; o >>= 1) {
-                    acc[h].x += __shfl_xor_sync(0xffffffffu, acc[h].x, o * CB);
-                    acc[h].y += __shfl_xor_sync(0xffffffffu, acc[h].y, o * CB);
-                }
-                if (sub == 0 && c < ncand && ra[h] < n) Y[(long long)(c0 + c) * ldy + ra[h]] = acc[h];
-            }
-        }
-        __syncthreads();                                                     // everybody is done with stage s
-        if (warp == 0) issue(b + 2LL * gridDim.x, s, nx0, nx1);
-    }
-}
-
 // persistent-style grid for the pipelined kernel: exactly the CTAs that are resident at once (occupancy query per instantiation),
 // every lane group walks many rows
 template <int CB, int SP_U, int MINB>
@@ -336,71 +166,17 @@ static unsigned spmm_pipe_grid(long long n) {
 
 }  // namespace
 
-// L2 residency of the interleaved copy.  The gathers hit P at random; one group of P at n = 1M is 64 MB, the matrix streams
-// 440 MB through the same L2 and (ncu, round 2) ~30 % of the gathered sectors missed and became random DRAM reads.  With
-// MAUS_SPMM_L2PERSIST (fraction of P marked persisting, e.g. 0.6) the groups are launched one by one, each with an access-policy
-// window over its own copy: persisting for P, streaming for everything else.
-static float spmm_l2_persist_ratio() {
-    static float ratio = -1.f;
-    if (ratio < 0.f) {
-        const char* e = getenv("MAUS_SPMM_L2PERSIST");
-        ratio = e ? (float)atof(e) : 0.f;
-        if (ratio > 0.f) {
-            int dev = 0; cudaGetDevice(&dev);
-            cudaDeviceProp prop;
-            if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0 ||
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) != cudaSuccess) {
-                cudaGetLastError(); ratio = 0.f;
-            }
-        }
-    }
-    return ratio;
-}
-
-template <class Launch>
-static cudaError_t spmm_launch_groups(const cplx* P, long long p_gstride, int groups, cudaStream_t stream, Launch launch) {
-    const float ratio = spmm_l2_persist_ratio();
-    if (ratio <= 0.f || p_gstride <= 0) { launch(0, groups); return cudaGetLastError(); }
-    int dev = 0; cudaGetDevice(&dev);
-    int max_win = 0; cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-    for (int g = 0; g < groups; ++g) {
-        cudaStreamAttrValue attr = {};
-        attr.accessPolicyWindow.base_ptr = const_cast<cplx*>(P + (long long)g * p_gstride);
-        size_t bytes = (size_t)p_gstride * sizeof(cplx);
-        if (max_win > 0 && bytes > (size_t)max_win) bytes = (size_t)max_win;
-        attr.accessPolicyWindow.num_bytes = bytes;
-        attr.accessPolicyWindow.hitRatio = ratio > 1.f ? 1.f : ratio;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-        launch(g, 1);
-    }
-    cudaStreamAttrValue off = {};
-    off.accessPolicyWindow.num_bytes = 0;
-    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &off);
-    return cudaGetLastError();
-}
-
 cudaError_t csr_spmm_packed4(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* P, long long p_gstride,
                              cplx* Y, long long ldy, long long n, int c0, int ctotal, int groups, cudaStream_t stream) {
     if (groups <= 0 || n <= 0) return cudaSuccess;
-    static int staged = -1;                  // MAUS_SPMM_STAGED=1: the shared-memory staged kernel (measured slower: 0.37 vs 0.33 ms)
-    if (staged < 0) { const char* e = getenv("MAUS_SPMM_STAGED"); staged = e ? atoi(e) : 0; }
-    if (staged) {
-        static int per_sm = 0;
-        if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_staged_kernel<4, 4>, ST_NT, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
-        const long long nblocks = (n + ST_RB - 1) / ST_RB, cap = (long long)MAUS_SM_COUNT_B200 * per_sm;
-        const unsigned gx = (unsigned)(nblocks < cap ? nblocks : cap);
-        return spmm_launch_groups(P, p_gstride, groups, stream, [&](int g0, int ng) {
-            csr_spmm_staged_kernel<4, 4><<<dim3(gx, (unsigned)ng), ST_NT, 0, stream>>>(rowptr, colidx, vals, P + (long long)g0 * p_gstride, p_gstride,
-                                                                                    Y, ldy, n, c0 + 4 * g0, ctotal);
-        });
-    }
-    const unsigned gx = spmm_pipe_grid<4, 3, 4>(n);
-    return spmm_launch_groups(P, p_gstride, groups, stream, [&](int g0, int ng) {
-        csr_spmm_packed_kernel<4, 3, 4><<<dim3(gx, (unsigned)ng), SP_NT, 0, stream>>>(rowptr, colidx, vals, P + (long long)g0 * p_gstride, p_gstride,
-                                                                                    Y, ldy, n, c0 + 4 * g0, ctotal);
-    });
+    // Measured alternatives that did not beat this kernel (round 2, 4 candidates, n = 1M, 0.29 - 0.33 ms): two rows of look-ahead
+    // (114 registers, 0.48 ms), 48 / 40-register builds with spills (0.49 / 0.82 ms), a shared-memory staged matrix stream with six
+    // gathers in flight per lane (commit 109fb77, 0.37 ms), an L2 persisting window over the interleaved copy (commit 1638896, 0.32 - 0.51 ms).
+    // ncu: l1tex 71 % busy (data return path 58 %), L2 36 %, DRAM 32 % -- the kernel sits at ~0.7 of the L1 limit of this
+    // access pattern (one 16-byte gather per lane, values broadcast to the four candidate lanes).
+    dim3 grid(spmm_pipe_grid<4, 3, 4>(n), (unsigned)groups);
+    csr_spmm_packed_kernel<4, 3, 4><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
+    return cudaGetLastError();
 }
 
 cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* V, long long ldv, cplx* Y,
