@@ -17,6 +17,7 @@ from .population import step_population
 REC_FIELDS = ("lambda_re", "lambda_im", "residual", "prev_residual", "alpha_re", "alpha_is_complex", "stuck", "retries",
               "resets", "w", "state", "hist_added", "lambda_is_real", "rng_drawn")
 NREC = len(REC_FIELDS)
+assert NREC % 2 == 0          # the vector part of a gathered row starts on a complex128 boundary
 
 
 class Shard:
@@ -158,7 +159,9 @@ def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, e
             continue
         for k, i in enumerate(range(r, len(live), shard.world)):
             row = gathered[r][k]
-            vec = row[NREC:].copy().view(np.complex128)
+            # a VIEW into the freshly gathered block (a new array every generation, 16-byte aligned at column NREC): no
+            # per-candidate copy of the 16 n bytes; the candidate replaces the vector object on its next step
+            vec = row[NREC:].view(np.complex128)
             _apply_record(live[i], row[:NREC], vec, eigen, State)
     _resync_host_rng(gathered, counts)
     return len(live)
