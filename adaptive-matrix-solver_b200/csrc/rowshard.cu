@@ -306,13 +306,35 @@ __global__ void rs_expand4_kernel(double* __restrict__ part, long long cand_stri
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-static void rs_p2p_release(RowShard* rs) {
+// Tear-down order matters: a segment must not be freed while a peer still has it mapped.  close = unmap the peers' segments,
+// free = release the own one; the collective variant puts a barrier before each phase (nobody writes any more / nobody maps any more).
+static void rs_p2p_close_peers(RowShard* rs) {
     for (int r = 0; r < rs->world && r < RS_MAXG; ++r)
-        if (r != rs->rank && rs->peer[r]) { cudaIpcCloseMemHandle(rs->peer[r]); }
+        if (r != rs->rank && rs->peer[r]) cudaIpcCloseMemHandle(rs->peer[r]);
     for (int r = 0; r < RS_MAXG; ++r) rs->peer[r] = nullptr;
+}
+static void rs_p2p_free_own(RowShard* rs) {
     cudaFree(rs->seg); rs->seg = nullptr; rs->seg_bytes = 0;
     cudaFree(rs->d_peer); rs->d_peer = nullptr;
     rs->p2p = false; rs->seg_C = 0; rs->seq_x = rs->seq_red = 0;
+}
+static void rs_p2p_release(RowShard* rs) { rs_p2p_close_peers(rs); rs_p2p_free_own(rs); }
+
+static int rs_barrier(maus_ctx* ctx, RowShard* rs) {
+    if (rs->world <= 1) return MAUS_OK;
+    ncclResult_t r = g_nccl.AllReduce(rs->d_err, rs->d_err, 1, ncclInt32, ncclMax, rs->comm, ctx->stream);
+    if (r != ncclSuccess) return maus_fail(ctx, MAUS_E_CUDA, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclAllReduce");
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return maus_fail(ctx, MAUS_E_CUDA, "rs_barrier", e);
+    return MAUS_OK;
+}
+// collective: every rank calls it at the same point
+static int rs_p2p_release_collective(maus_ctx* ctx, RowShard* rs) {
+    int rc = rs_barrier(ctx, rs); if (rc) return rc;          // nobody still writes into a peer's segment
+    rs_p2p_close_peers(rs);
+    if ((rc = rs_barrier(ctx, rs))) return rc;                // nobody still maps this rank's segment
+    rs_p2p_free_own(rs);
+    return MAUS_OK;
 }
 
 void maus_rowshard_free(maus_ctx* ctx) {
@@ -418,12 +440,7 @@ extern "C" int maus_set_csr_rowblock(maus_ctx* ctx, int64_t n, int64_t row0, int
         cudaFree(rs->xfull); cudaFree(rs->pack); cudaFree(rs->V); cudaFree(rs->X); cudaFree(rs->Y); cudaFree(rs->b);
         rs->xfull = rs->pack = rs->V = rs->X = rs->Y = rs->b = nullptr; rs->pack_elems = 0; rs->Ccap = 0; rs->b_set = false;
         if (rs->seg) {
-            // peers may still hold mappings of the old segment: release only after everybody arrived here
-            if (rs->world > 1) {
-                MAUS_NCCL(ctx, g_nccl.AllReduce(rs->d_err, rs->d_err, 1, ncclInt32, ncclMax, rs->comm, ctx->stream));
-                MAUS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            }
-            rs_p2p_release(rs);
+            int rc = rs_p2p_release_collective(ctx, rs); if (rc) return rc;
             rs->p2p_tried = false;
         }
     }
@@ -449,13 +466,7 @@ static int rs_p2p_setup(maus_ctx* ctx, RowShard* rs, long long C) {
     if (force && atoi(force)) { rs->p2p = false; rs->p2p_tried = true; return MAUS_OK; }
     if (rs->world > RS_MAXG) { rs->p2p = false; rs->p2p_tried = true; return MAUS_OK; }
     cudaStream_t st = ctx->stream;
-    if (rs->seg) {
-        if (rs->world > 1) {
-            MAUS_NCCL(ctx, g_nccl.AllReduce(rs->d_err, rs->d_err, 1, ncclInt32, ncclMax, rs->comm, st));   // barrier: nobody still writes into the old segment
-            MAUS_CUDA(ctx, cudaStreamSynchronize(st));
-        }
-        rs_p2p_release(rs);
-    }
+    if (rs->seg) { int rc = rs_p2p_release_collective(ctx, rs); if (rc) return rc; }
     rs->p2p_tried = true;
     const long long groups = (C + 3) / 4;
     rs->seg_C = groups * 4;
@@ -510,7 +521,7 @@ static int rs_p2p_setup(maus_ctx* ctx, RowShard* rs, long long C) {
         MAUS_CUDA(ctx, cudaStreamSynchronize(st));
         cudaFree(dflag);
     }
-    if (!ok) { rs_p2p_release(rs); return MAUS_OK; }                     // NCCL transport
+    if (!ok) return rs_p2p_release_collective(ctx, rs);                  // every rank takes this branch: NCCL transport
     MAUS_CUDA(ctx, cudaMalloc(&rs->d_peer, sizeof(void*) * RS_MAXG));
     MAUS_CUDA(ctx, cudaMemcpy(rs->d_peer, rs->peer, sizeof(void*) * RS_MAXG, cudaMemcpyHostToDevice));
     rs->p2p = true;
