@@ -196,7 +196,11 @@ extern "C" int maus_create(maus_ctx** out, int device) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return MAUS_E_CUDA; }
     if (prop.major != 10) { delete ctx; return MAUS_E_CUDA; }   // sm_100a only
     ctx->sm_count = prop.multiProcessorCount;
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return MAUS_E_CUDA; }
+    {
+        int lo = 0, hi = 0;                      // highest priority: auxiliary streams of the context (rowshard.cu) run beside it, not before it
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi)) != cudaSuccess) { delete ctx; return MAUS_E_CUDA; }
+    }
     *out = ctx;
     return MAUS_OK;
 }

@@ -59,12 +59,13 @@ constexpr int RS_RED_COMP = 4;         // doubles per candidate and reduction
 constexpr int RS_PUSH_ROWS = 64;       // rows per CTA of the push kernel: 64 x 4 x 16 B = one 4 KB piece per destination
 constexpr long long RS_SPIN_LIMIT = 40000000000LL;  // ~20 s of SM clocks: a lost peer sets the error flag instead of hanging the GPU
 
+constexpr int RS_MAXGRP = 256;         // groups of 4 candidates per matvec (C <= 1024)
 // flag words at the head of the segment (unsigned long long each)
-constexpr int RS_F_XREADY = 0;                          // [2][RS_MAXG]  push of buffer b by rank r complete (sequence number)
-constexpr int RS_F_XDONE = 2 * RS_MAXG;                 // [RS_MAXG]     rank r finished reading its copy for matvec seq
-constexpr int RS_F_RED = 3 * RS_MAXG;                   // [RS_RED_SLOTS][RS_MAXG]
-constexpr int RS_F_WORDS = (3 + RS_RED_SLOTS) * RS_MAXG;
-constexpr size_t RS_FLAG_BYTES = 4096;
+constexpr int RS_F_XDONE = 0;                           // [RS_MAXG]     rank r finished reading its copy for matvec seq
+constexpr int RS_F_RED = RS_MAXG;                       // [RS_RED_SLOTS][RS_MAXG]
+constexpr int RS_F_XREADY = (1 + RS_RED_SLOTS) * RS_MAXG;   // [2][RS_MAXGRP][RS_MAXG]  push of group g of buffer b by rank r complete
+constexpr int RS_F_WORDS = RS_F_XREADY + 2 * RS_MAXGRP * RS_MAXG;
+constexpr size_t RS_FLAG_BYTES = 128 * 1024;
 static_assert(RS_F_WORDS * 8 <= (int)RS_FLAG_BYTES, "flag area");
 
 struct RowShard {
@@ -88,6 +89,8 @@ struct RowShard {
     size_t off_red = 0, off_x = 0, xbuf_bytes = 0;
     long long seg_C = 0;                            // candidates the segment was sized for
     unsigned long long seq_x = 0, seq_red = 0;
+    cudaStream_t push_stream = nullptr;             // the pushes of a matvec run beside the SpMMs of its earlier groups
+    cudaEvent_t ev_input = nullptr;                 // matvec input complete on the context's stream
     unsigned int* d_counter = nullptr;              // last-CTA-done counter of the push kernel
     int* d_err = nullptr;                           // set by a spin loop that hit RS_SPIN_LIMIT
     // gather buffers of maus_gather
@@ -130,11 +133,12 @@ __device__ __forceinline__ void spin_until(const unsigned long long* flag, unsig
 }
 __device__ __forceinline__ unsigned long long* seg_flags(void* base) { return reinterpret_cast<unsigned long long*>(base); }
 
-// pack + all-gather in one kernel: the local slices of the C vectors -> interleaved [group][row0 + i][4] in EVERY rank's segment.
-// grid (ceil(nloc / RS_PUSH_ROWS), groups), 256 threads.
+// pack + all-gather in one kernel: the local slices of the 4 vectors of group g -> interleaved [g][row0 + i][4] in EVERY rank's
+// segment.  grid ceil(nloc / RS_PUSH_ROWS), 256 threads; one launch per group on the push stream, so that the SpMM of group g
+// (context stream) runs while the groups after it are still crossing NVLink.
 __global__ void __launch_bounds__(256) rs_push_pack_kernel(const cplx* __restrict__ v, long long ldv, int C, long long nloc,
                                                            long long row0, long long n, void* const* __restrict__ peer,
-                                                           size_t off_xbuf, int buf, int rank, int G, unsigned long long seq,
+                                                           size_t off_xbuf, int buf, int g, int rank, int G, unsigned long long seq,
                                                            unsigned int* counter, int* err) {
     __shared__ cplx tile[4][RS_PUSH_ROWS + 1];
     __shared__ int is_last;
@@ -142,43 +146,45 @@ __global__ void __launch_bounds__(256) rs_push_pack_kernel(const cplx* __restric
     // the copy being overwritten was last read by matvec seq - 2 (two buffers): every peer must have finished that one
     if (seq > 2 && t < G) spin_until(seg_flags(peer[rank]) + RS_F_XDONE + t, seq - 2, err);
     __syncthreads();
-    const int g = blockIdx.y;
-    const long long i0 = (long long)blockIdx.x * RS_PUSH_ROWS;
-    {
-        const int c = t / RS_PUSH_ROWS, i = t % RS_PUSH_ROWS;          // 64 consecutive rows of one candidate: 1 KB coalesced
-        const int cand = g * 4 + c;
-        tile[c][i] = (cand < C && i0 + i < nloc) ? v[(long long)cand * ldv + i0 + i] : cmake(0.0, 0.0);
-    }
-    __syncthreads();
-    {
-        const int i = t >> 2, c = t & 3;                               // destination order: 256 consecutive elements = 4 KB
-        if (i0 + i < nloc) {
-            const cplx val = tile[c][i];
-            const long long off = ((long long)g * n + row0 + i0 + i) * 4 + c;
-            for (int k = 0; k < G; ++k) {
-                const int d = (rank + k) % G;                          // every rank starts with its own copy: spreads the NVLink ports
-                cplx* dst = reinterpret_cast<cplx*>(static_cast<unsigned char*>(peer[d]) + off_xbuf) + off;
-                *dst = val;
+    // a bounded grid walks the row tiles: the kernel is NVLink-bound, it must not take the SM slots the SpMM of the earlier
+    // groups (context stream) is waiting for
+    for (long long i0 = (long long)blockIdx.x * RS_PUSH_ROWS; i0 < nloc; i0 += (long long)gridDim.x * RS_PUSH_ROWS) {
+        {
+            const int c = t / RS_PUSH_ROWS, i = t % RS_PUSH_ROWS;      // 64 consecutive rows of one candidate: 1 KB coalesced
+            const int cand = g * 4 + c;
+            tile[c][i] = (cand < C && i0 + i < nloc) ? v[(long long)cand * ldv + i0 + i] : cmake(0.0, 0.0);
+        }
+        __syncthreads();
+        {
+            const int i = t >> 2, c = t & 3;                           // destination order: 256 consecutive elements = 4 KB
+            if (i0 + i < nloc) {
+                const cplx val = tile[c][i];
+                const long long off = ((long long)g * n + row0 + i0 + i) * 4 + c;
+                for (int k = 0; k < G; ++k) {
+                    const int d = (rank + k) % G;                      // every rank starts with its own copy: spreads the NVLink ports
+                    cplx* dst = reinterpret_cast<cplx*>(static_cast<unsigned char*>(peer[d]) + off_xbuf) + off;
+                    *dst = val;
+                }
             }
         }
+        __syncthreads();                                               // the tile is rewritten by the next iteration
     }
     __threadfence_system();
     __syncthreads();
     if (t == 0) {
-        const unsigned int total = gridDim.x * gridDim.y;
-        is_last = (atomicAdd(counter, 1u) == total - 1) ? 1 : 0;
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
     if (is_last) {
         if (t == 0) *counter = 0;
         __threadfence_system();
-        if (t < G) st_release_sys(seg_flags(peer[t]) + RS_F_XREADY + buf * RS_MAXG + rank, seq);
+        if (t < G) st_release_sys(seg_flags(peer[t]) + RS_F_XREADY + (buf * RS_MAXGRP + g) * RS_MAXG + rank, seq);
     }
 }
 
-// consumer side of the all-gather: wait until every rank's piece of buffer `buf` has arrived
-__global__ void rs_wait_x_kernel(void* const* __restrict__ peer, int buf, int rank, int G, unsigned long long seq, int* err) {
-    if ((int)threadIdx.x < G) spin_until(seg_flags(peer[rank]) + RS_F_XREADY + buf * RS_MAXG + threadIdx.x, seq, err);
+// consumer side of the all-gather: wait until every rank's piece of group g of buffer `buf` has arrived
+__global__ void rs_wait_x_kernel(void* const* __restrict__ peer, int buf, int g, int rank, int G, unsigned long long seq, int* err) {
+    if ((int)threadIdx.x < G) spin_until(seg_flags(peer[rank]) + RS_F_XREADY + (buf * RS_MAXGRP + g) * RS_MAXG + threadIdx.x, seq, err);
 }
 // after the SpMM: tell every peer this rank no longer reads the copy of matvec `seq`
 __global__ void rs_done_x_kernel(void* const* __restrict__ peer, int rank, int G, unsigned long long seq) {
@@ -346,6 +352,8 @@ void maus_rowshard_free(maus_ctx* ctx) {
     cudaFree(rs->jac); cudaFree(rs->status); cudaFree(rs->iters); cudaFree(rs->gsend); cudaFree(rs->grecv);
     rs_p2p_release(rs);
     cudaFree(rs->d_counter); cudaFree(rs->d_err);
+    if (rs->push_stream) { cudaStreamSynchronize(rs->push_stream); cudaStreamDestroy(rs->push_stream); }
+    if (rs->ev_input) cudaEventDestroy(rs->ev_input);
     if (rs->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(rs->comm);
     delete rs;
     ctx->rowshard = nullptr;
@@ -371,6 +379,12 @@ extern "C" int maus_dist_init(maus_ctx* ctx, const char* libpath, int rank, int 
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     MAUS_NCCL(ctx, g_nccl.CommInitRank(&rs->comm, world, id, rank));
+    {
+        int lo = 0, hi = 0;                                            // the pushes yield SM slots to the context's (high-priority) stream
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        MAUS_CUDA(ctx, cudaStreamCreateWithPriority(&rs->push_stream, cudaStreamNonBlocking, lo));
+    }
+    MAUS_CUDA(ctx, cudaEventCreateWithFlags(&rs->ev_input, cudaEventDisableTiming));
     MAUS_CUDA(ctx, cudaMalloc(&rs->d_counter, sizeof(unsigned int)));
     MAUS_CUDA(ctx, cudaMalloc(&rs->d_err, sizeof(int)));
     MAUS_CUDA(ctx, cudaMemset(rs->d_counter, 0, sizeof(unsigned int)));
@@ -462,12 +476,12 @@ extern "C" int maus_set_csr_rowblock(maus_ctx* ctx, int64_t n, int64_t row0, int
 
 // (re)build the symmetric segment for C candidates and map every peer's copy.  Collective: all ranks call it with the same C.
 static int rs_p2p_setup(maus_ctx* ctx, RowShard* rs, long long C) {
-    const char* force = getenv("MAUS_RS_NCCL");
-    if (force && atoi(force)) { rs->p2p = false; rs->p2p_tried = true; return MAUS_OK; }
-    if (rs->world > RS_MAXG) { rs->p2p = false; rs->p2p_tried = true; return MAUS_OK; }
     cudaStream_t st = ctx->stream;
     if (rs->seg) { int rc = rs_p2p_release_collective(ctx, rs); if (rc) return rc; }
     rs->p2p_tried = true;
+    const char* force = getenv("MAUS_RS_NCCL");
+    if (force && atoi(force)) { rs->p2p = false; return MAUS_OK; }
+    if (rs->world > RS_MAXG || C > 4LL * RS_MAXGRP) { rs->p2p = false; return MAUS_OK; }
     const long long groups = (C + 3) / 4;
     rs->seg_C = groups * 4;
     rs->off_red = RS_FLAG_BYTES;
@@ -589,15 +603,23 @@ static int rs_matvec(maus_ctx* ctx, RowShard* rs, const cplx* v, long long ldv, 
         const unsigned long long seq = ++rs->seq_x;
         const int buf = (int)(seq & 1);
         const size_t off = rs->off_x + (size_t)buf * rs->xbuf_bytes;
-        dim3 grid((unsigned)((rs->nloc + RS_PUSH_ROWS - 1) / RS_PUSH_ROWS), (unsigned)groups);
-        rs_push_pack_kernel<<<grid, 256, 0, st>>>(v, ldv, (int)C, rs->nloc, rs->row0, rs->n, rs->d_peer, off, buf, rs->rank, rs->world,
-                                                  seq, rs->d_counter, rs->d_err);
-        rs_wait_x_kernel<<<1, 32, 0, st>>>(rs->d_peer, buf, rs->rank, rs->world, seq, rs->d_err);
+        const long long tiles = (rs->nloc + RS_PUSH_ROWS - 1) / RS_PUSH_ROWS;
+        const unsigned gpush = (unsigned)std::min<long long>(tiles, 2LL * MAUS_SM_COUNT_B200);
         const cplx* P = reinterpret_cast<const cplx*>(rs->seg + off);
-        MAUS_CUDA(ctx, csr_spmm_packed4(rs->rowptr, rs->colidx, rs->vals, P, rs->n * 4, z, ldz, rs->nloc, 0, (int)C, groups, st));
+        // pushes on their own stream, behind the producer of v; group g's SpMM only waits for group g's pieces
+        MAUS_CUDA(ctx, cudaEventRecord(rs->ev_input, st));
+        MAUS_CUDA(ctx, cudaStreamWaitEvent(rs->push_stream, rs->ev_input, 0));
+        for (int g = 0; g < groups; ++g)
+            rs_push_pack_kernel<<<gpush, 256, 0, rs->push_stream>>>(v, ldv, (int)C, rs->nloc, rs->row0, rs->n, rs->d_peer, off, buf, g, rs->rank,
+                                                                    rs->world, seq, rs->d_counter, rs->d_err);
+        for (int g = 0; g < groups; ++g) {
+            rs_wait_x_kernel<<<1, 32, 0, st>>>(rs->d_peer, buf, g, rs->rank, rs->world, seq, rs->d_err);
+            MAUS_CUDA(ctx, csr_spmm_packed4(rs->rowptr, rs->colidx, rs->vals, P + (long long)g * rs->n * 4, rs->n * 4, z, ldz, rs->nloc, 4 * g,
+                                            (int)C, 1, st));
+        }
         rs_done_x_kernel<<<1, 32, 0, st>>>(rs->d_peer, rs->rank, rs->world, seq);
         MAUS_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 4;
+        ctx->launches += 3 * groups + 1;
     } else {
         ncclResult_t r1 = g_nccl.GroupStart();
         ncclResult_t r2 = ncclSuccess;
