@@ -539,6 +539,9 @@ int maus_lu_solve(maus_ctx* ctx, long long C, const cplx* sigma, const double* p
             p.C = C; p.ldc = n; p.strideC = strideW;
             p.M = M; p.N = N; p.K = K; p.batch = nb; p.beta = beta; p.negate = negate;
             p.algo3m = lu_use_3m();
+            // 49 .. 64 columns (the 64-wide leaf updates): two full 32-wide tiles instead of a 48-wide and a 16/48-filled one
+            // (the 32-wide tile runs at ~0.83 of the 48-wide one's rate, so it only pays where the padding exceeds that)
+            p.tile_n = (N > 48 && N <= 64) ? 32 : 0;
             int h = prof_begin(ctx, MAUS_PROF_LU_GEMM, 8.0 * M * (double)N * K * nb);
             prof_tag(ctx, h, M, N, K, nb);
             cudaError_t e = zgemm_dmma_launch(p, st);
