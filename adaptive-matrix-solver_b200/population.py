@@ -12,8 +12,9 @@ It performs, for every live EIGENVALUE (non-Hermitian) / SOLVE_LINEAR_SYSTEM can
 the reference mutates, so ``_update_global_diagnostics`` / ``_adjust_global_strategy`` / ``_manage_candidates`` run
 unmodified afterwards.  All numerics (Rayleigh quotient, shifted solve, mix, normalise, residual) run in ONE fused
 CUDA call for the whole population; only the rare failures walk the Psi ladder (AMS:43-104) through the granular
-calls.  SVD candidates run the batched power sweep of ``svd.cu``; Hermitian-eigen candidates are
-passed to the reference method untouched.
+calls.  SVD candidates run the batched power sweep of ``svd.cu``; dense Hermitian-eigen candidates
+share one device eigendecomposition (8f-3); sparse Hermitian ones (eigsh) are passed to the reference method untouched.  With
+``engine.enable_row_sharding`` a sparse problem on the GMRES path runs on the row-sharded operator (BASELINE config 5).
 
 Deliberate deviations (DESIGN.md section "Deviations"): the dense Psi perturbation (AMS:49) comes from a
 counter-based device RNG, not from the global numpy stream; host RNG draws therefore happen only for the
@@ -462,9 +463,10 @@ def install_dropin(ams_module, engine):
 
 def _step_group_hermitian(cands, M, b, strat_params, problem_knowledge, engine, State):
     """Dense Hermitian shortcut (AMS:155-186) for a whole group.  The reference calls ``sla.eigh(current_matrix_A)`` inside
-    EVERY candidate's step -- C identical O(n^3) factorizations per generation.  Here the same LAPACK call runs ONCE (same
-    eigenpairs, bit for bit), the similarity scores |v_k^H E| of all candidates are one device GEMM (``engine.project``) and
-    the residuals one batched device pass.  A failing eigh falls back to the reference method per candidate (AMS:182-185)."""
+    EVERY candidate's step -- C identical O(n^3) factorizations per generation.  Here ONE eigendecomposition per matrix runs
+    on the device (``engine.heev``: cyclic Jacobi, heev.cu; same eigenpairs to rounding, vectors up to a phase), the
+    similarity scores |v_k^H E| of all candidates are one device GEMM (``engine.project``) and the residuals one batched
+    device pass.  A failing decomposition falls back to the reference method per candidate (AMS:182-185)."""
     import scipy.linalg as sla
     cache = getattr(engine, "_eigh_cache", None)
     try:
