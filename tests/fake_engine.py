@@ -28,6 +28,15 @@ class FakeEngine:
     def upload_vectors(self, V):
         pass
 
+    # set-up diagnostics (numpy stand-ins of maus_diag_dense / maus_cond2_estimate)
+    def diag_dense(self, rtol=1e-5, atol=1e-8):
+        A = self.A[0]
+        return int(np.count_nonzero(A)), bool(np.allclose(A, A.conj().T, rtol=rtol, atol=atol)), bool(np.allclose(A, A.T, rtol=rtol, atol=atol))
+
+    def cond2_estimate(self, power_iters=40, inverse_iters=8, start=None):
+        s = np.linalg.svd(self.A[0], compute_uv=False)
+        return float(s[0]), float(s[-1]), 0 if s[-1] > 0 else 1
+
     def solve_shifted(self, sigma, psi, rng_key=None, method=0, use_jacobi=None, RHS=None, rhs_shared=False, want_x=True):
         C_ = len(sigma)          # only reached for candidates in fail_ids: every attempt of the ladder fails
         return None, np.full(C_, 1, dtype=np.int32), np.zeros(C_, dtype=np.int32)

@@ -197,3 +197,28 @@ def test_initial_strategy_mirrors_the_reference_for_its_own_scenarios():
                 assert s.strat_params[k] == v, (pt, k)
             for k, v in know.items():
                 assert s.problem_knowledge[k] == v, (pt, k)
+
+
+def test_install_diagnostics_drives_the_reference_constructor():
+    """diagnostics.install_diagnostics rebinds MAUS_Solver._diagnose_matrix_initial (AMS:345 calls it through self): the REAL
+    constructor must build the same diag_info / strategy / problem_knowledge from the engine-backed diagnosis as from its own
+    numpy one (dense, Hermitian, ill-conditioned and sparse inputs)."""
+    import scipy.sparse as sp
+    from adaptive_matrix_solver_b200.diagnostics import install_diagnostics
+    from fake_engine import FakeEngine
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((30, 30)) + 1j * rng.standard_normal((30, 30))
+    U, _, Vh = np.linalg.svd(G)
+    mats = [G, G + G.conj().T, (U * np.logspace(0, -9, 30)) @ Vh, sp.random(30, 30, density=0.2, random_state=1, format="csc") + sp.eye(30, format="csc")]
+    for M in mats:
+        ref_mod = load_reference(gmres_shim=True, name="ams_diag_ref")
+        gpu_mod = install_diagnostics(load_reference(gmres_shim=True, name="ams_diag_gpu"), FakeEngine())
+        np.random.seed(2); random.seed(2)
+        a = quiet(ref_mod.MAUS_Solver, M, problem_type=ref_mod.ProblemType.EIGENVALUE, initial_num_candidates=2)
+        np.random.seed(2); random.seed(2)
+        b = quiet(gpu_mod.MAUS_Solver, M, problem_type=gpu_mod.ProblemType.EIGENVALUE, initial_num_candidates=2)
+        for k in ("is_hermitian", "is_complex_symmetric", "is_sparse_init", "is_singular"):
+            assert a.diag_info[k] == b.diag_info[k], k
+        ca, cb = a.diag_info["condition_number"], b.diag_info["condition_number"]
+        assert (np.isinf(ca) and np.isinf(cb)) or abs(ca - cb) <= 1e-8 * ca
+        assert a.strat_params == b.strat_params and a.problem_knowledge == b.problem_knowledge
