@@ -137,6 +137,7 @@ int maus_ensure_population(maus_ctx* ctx, long long C) {
     if ((rc = ensure(ctx, &ctx->resid, cap))) return rc;
     if ((rc = ensure(ctx, &ctx->mixnorm, cap))) return rc;
     if ((rc = ensure(ctx, &ctx->vscratch, (long long)vec_scratch_doubles(cap)))) return rc;
+    MAUS_CUDA(ctx, cudaMemset(ctx->vscratch, 0, vec_scratch_doubles(cap) * 8));      // block-done counters start at zero
     if ((rc = ensure(ctx, &ctx->keys, cap))) return rc;
     if ((rc = ensure(ctx, &ctx->status, cap))) return rc;
     if ((rc = ensure(ctx, &ctx->iters, cap))) return rc;
@@ -635,7 +636,7 @@ extern "C" int maus_rq(maus_ctx* ctx, int64_t C, const double* V, double* lambda
     if (V) MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->V, V, (size_t)C * n * sizeof(cplx), cudaMemcpyHostToDevice, st));
     if ((rc = maus_apply_matrix(ctx, 0, ctx->V, n, ctx->Y, n, C))) return rc;
     { int hv = prof_begin(ctx, MAUS_PROF_VEC, 32.0 * n * (double)C);
-    MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, nullptr, ctx->vscratch, st));
+    MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, nullptr, ctx->vscratch, st, (int)ctx->Ccap));
       prof_end(ctx, hv); }
     ctx->launches += 1;
     if (lambda_out) MAUS_CUDA(ctx, cudaMemcpyAsync(lambda_out, ctx->lambda, (size_t)C * sizeof(cplx), cudaMemcpyDeviceToHost, st));
@@ -727,7 +728,7 @@ static int residual_device(maus_ctx* ctx, long long C, int problem_type, int res
     if (problem_type == MAUS_SOLVE_LINEAR_SYSTEM && !ctx->b_set) return maus_fail(ctx, MAUS_E_STATE, "rhs not set");
     { int hv = prof_begin(ctx, MAUS_PROF_VEC, 32.0 * ctx->n * (double)C);
     MAUS_CUDA(ctx, vec_residual_finish(ctx->V, ctx->Y, (int)ctx->n, (int)C, problem_type, ctx->lambda, ctx->b, ctx->resid,
-                                       ctx->vscratch, ctx->stream));
+                                       ctx->vscratch, ctx->stream, (int)ctx->Ccap));
       prof_end(ctx, hv); }
     ctx->launches += 2;
     return MAUS_OK;
@@ -808,7 +809,7 @@ extern "C" int maus_step(maus_ctx* ctx, int64_t C, int problem_type, int method,
         // AMS:264-270: lambda = RQ(v); sigma = lambda
         if ((rc = maus_apply_matrix(ctx, 0, ctx->V, n, ctx->Y, n, C))) return rc;
         { int hv = prof_begin(ctx, MAUS_PROF_VEC, 32.0 * n * (double)C);
-        MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, ctx->status, ctx->vscratch, st));
+        MAUS_CUDA(ctx, vec_rq_finish(ctx->V, ctx->Y, (int)n, (int)C, ctx->lambda, ctx->vnorm2, ctx->status, ctx->vscratch, st, (int)ctx->Ccap));
           prof_end(ctx, hv); }
         ctx->launches += 1;
         MAUS_CUDA(ctx, cudaMemcpyAsync(ctx->sigma, ctx->lambda, (size_t)C * sizeof(cplx), cudaMemcpyDeviceToDevice, st));

@@ -245,12 +245,12 @@ __device__ __forceinline__ void vmb_range(int n, int nblk, int blk, int& i0, int
 }
 __device__ __forceinline__ double vmb_sum(const double* part, int nblk, int k) {
     double s = 0.0;
-    for (int q = 0; q < nblk; ++q) s += part[q * 4 + k];
+    for (int q = 0; q < nblk; ++q) s += __ldcg(&part[q * 4 + k]);      // L2: written by other blocks (of this launch, when fused)
     return s;
 }
 __device__ __forceinline__ double vmb_max(const double* part, int nblk, int k) {
     double s = 0.0;
-    for (int q = 0; q < nblk; ++q) s = fmax(s, part[q * 4 + k]);
+    for (int q = 0; q < nblk; ++q) s = fmax(s, __ldcg(&part[q * 4 + k]));
     return s;
 }
 
@@ -258,7 +258,36 @@ __device__ __forceinline__ double vmb_max(const double* part, int nblk, int k) {
 // sum of the one-CTA kernels is only recomputed when the plain sum left the safe range (never for normalised vectors).
 __device__ __forceinline__ bool vmb_ss_safe(double ss) { return isfinite(ss) && ss > 1e-290; }
 
-__global__ void __launch_bounds__(RED_NT) rq_part_kernel(const cplx* __restrict__ V, const cplx* __restrict__ Y, int n, double* scratch) {
+// block-done counters live behind the partials: scratch[C * VMB_MAXBLK * 4 + c] (zero-initialised, reset by the last block)
+__device__ __forceinline__ unsigned int* vmb_counter(double* scratch, int C, int c) {
+    return reinterpret_cast<unsigned int*>(scratch + (long long)C * VMB_MAXBLK * 4 + c);
+}
+// true in every thread of the LAST block of candidate c to finish (the partials of all blocks are then visible to it)
+__device__ __forceinline__ bool vmb_last_block(double* scratch, int C, int c) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int* cnt = vmb_counter(scratch, C, c);
+        const bool last = atomicAdd(cnt, 1u) == gridDim.x - 1;
+        if (last) *cnt = 0;
+        s_last = last ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+__device__ __forceinline__ void rq_final_body(const double* part, int nblk, int c, cplx* lambda, double* vnorm2, int* status) {
+    const double nr = vmb_sum(part, nblk, 0), ni = vmb_sum(part, nblk, 1), d = vmb_sum(part, nblk, 2);
+    vnorm2[c] = d;
+    lambda[c] = (fabs(d) < 1e-12) ? cmake(0.0, 0.0) : cmake(nr / d, ni / d);     // AMS:265-268
+    if (status && sqrt(d) < 1e-10) status[c] = MAUS_ST_V_COLLAPSED;              // AMS:259
+}
+
+// fuse_C > 0: the last block of a candidate to finish also does the final reduction (fixed order over the blocks, whichever
+// block it is): one launch instead of part + final
+__global__ void __launch_bounds__(RED_NT) rq_part_kernel(const cplx* __restrict__ V, const cplx* __restrict__ Y, int n, double* scratch,
+                                                         int fuse_C, cplx* lambda, double* vnorm2, int* status) {
     __shared__ double sh[RED_NT / 32];
     const int c = blockIdx.y;
     int i0, i1; vmb_range(n, gridDim.x, blockIdx.x, i0, i1);
@@ -285,15 +314,13 @@ __global__ void __launch_bounds__(RED_NT) rq_part_kernel(const cplx* __restrict_
         double* o = scratch + ((long long)c * VMB_MAXBLK + blockIdx.x) * 4;
         o[0] = nr; o[1] = ni; o[2] = d;
     }
+    if (fuse_C > 0 && vmb_last_block(scratch, fuse_C, c) && threadIdx.x == 0)
+        rq_final_body(scratch + (long long)c * VMB_MAXBLK * 4, gridDim.x, c, lambda, vnorm2, status);
 }
 __global__ void rq_final_kernel(const double* __restrict__ scratch, int nblk, int C, cplx* lambda, double* vnorm2, int* status) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double* part = scratch + (long long)c * VMB_MAXBLK * 4;
-    const double nr = vmb_sum(part, nblk, 0), ni = vmb_sum(part, nblk, 1), d = vmb_sum(part, nblk, 2);
-    vnorm2[c] = d;
-    lambda[c] = (fabs(d) < 1e-12) ? cmake(0.0, 0.0) : cmake(nr / d, ni / d);     // AMS:265-268
-    if (status && sqrt(d) < 1e-10) status[c] = MAUS_ST_V_COLLAPSED;              // AMS:259
+    rq_final_body(scratch + (long long)c * VMB_MAXBLK * 4, nblk, c, lambda, vnorm2, status);
 }
 
 // pass 1: v <- (1-a) v + a x; per block: max |component| -> part[0], plain sum of squares -> part[1]
@@ -374,8 +401,37 @@ __global__ void mix_preset_kernel(const int* __restrict__ status, int C, double*
 }
 
 // residual, one pass: r = y - lambda v (eigen) / y - b (linear); max |component|, plain sum of squares, NaN flag of y and v
+// final value of candidate c from the partials of nblk blocks; executed by a whole block (the rare scaled recomputation walks the vector)
+__device__ void res_final_body(const cplx* __restrict__ V, const cplx* __restrict__ Y, int n, int problem_type, const cplx* __restrict__ lambda,
+                               const cplx* __restrict__ b, const double* part, int nblk, int c, double* resid, double* sh) {
+    const double amax = vmb_max(part, nblk, 0), ss = vmb_sum(part, nblk, 1), bad = vmb_max(part, nblk, 3);
+    double out;
+    if (bad > 0.0) out = nan("");                            // np.linalg.norm propagates NaN (fmax would drop it)
+    else if (!(amax > 0.0) || !isfinite(amax)) out = amax;
+    else if (vmb_ss_safe(ss)) out = sqrt(ss);
+    else {
+        // rare: recompute with the scaled sum (this block alone walks the vector)
+        const cplx* v = V + (long long)c * n;
+        const cplx* y = Y + (long long)c * n;
+        const bool eig = problem_type == MAUS_EIGENVALUE;
+        const cplx lam = eig ? lambda[c] : cmake(0.0, 0.0);
+        const double inv = 1.0 / amax;
+        double s2 = 0.0;
+        for (int i = threadIdx.x; i < n; i += RED_NT) {
+            cplx r = y[i];
+            if (eig) cfms(r, lam, v[i]); else r = csub(r, b[i]);
+            const double p = r.x * inv, q = r.y * inv;
+            s2 = fma(p, p, s2); s2 = fma(q, q, s2);
+        }
+        s2 = block_sum(s2, sh);
+        out = amax * sqrt(s2);
+    }
+    if (threadIdx.x == 0) resid[c] = out;
+}
+
 __global__ void __launch_bounds__(RED_NT) res_part_kernel(const cplx* __restrict__ V, const cplx* __restrict__ Y, int n, int problem_type,
-                                                          const cplx* __restrict__ lambda, const cplx* __restrict__ b, double* scratch) {
+                                                          const cplx* __restrict__ lambda, const cplx* __restrict__ b, double* scratch,
+                                                          int fuse_C, double* resid) {
     __shared__ double sh[RED_NT / 32];
     const int c = blockIdx.y;
     int i0, i1; vmb_range(n, gridDim.x, blockIdx.x, i0, i1);
@@ -406,36 +462,15 @@ __global__ void __launch_bounds__(RED_NT) res_part_kernel(const cplx* __restrict
         double* o = scratch + ((long long)c * VMB_MAXBLK + blockIdx.x) * 4;
         o[0] = amax; o[1] = ss; o[3] = bad;
     }
+    if (fuse_C > 0 && vmb_last_block(scratch, fuse_C, c))
+        res_final_body(V, Y, n, problem_type, lambda, b, scratch + (long long)c * VMB_MAXBLK * 4, gridDim.x, c, resid, sh);
 }
 __global__ void __launch_bounds__(RED_NT) res_final_kernel(const cplx* __restrict__ V, const cplx* __restrict__ Y, int n, int problem_type,
                                                            const cplx* __restrict__ lambda, const cplx* __restrict__ b,
                                                            const double* __restrict__ scratch, int nblk, double* resid) {
     __shared__ double sh[RED_NT / 32];
     const int c = blockIdx.x;
-    const double* part = scratch + (long long)c * VMB_MAXBLK * 4;
-    const double amax = vmb_max(part, nblk, 0), ss = vmb_sum(part, nblk, 1), bad = vmb_max(part, nblk, 3);
-    double out;
-    if (bad > 0.0) out = nan("");                            // np.linalg.norm propagates NaN (fmax would drop it)
-    else if (!(amax > 0.0) || !isfinite(amax)) out = amax;
-    else if (vmb_ss_safe(ss)) out = sqrt(ss);
-    else {
-        // rare: recompute with the scaled sum (this block alone walks the vector)
-        const cplx* v = V + (long long)c * n;
-        const cplx* y = Y + (long long)c * n;
-        const bool eig = problem_type == MAUS_EIGENVALUE;
-        const cplx lam = eig ? lambda[c] : cmake(0.0, 0.0);
-        const double inv = 1.0 / amax;
-        double s2 = 0.0;
-        for (int i = threadIdx.x; i < n; i += RED_NT) {
-            cplx r = y[i];
-            if (eig) cfms(r, lam, v[i]); else r = csub(r, b[i]);
-            const double p = r.x * inv, q = r.y * inv;
-            s2 = fma(p, p, s2); s2 = fma(q, q, s2);
-        }
-        s2 = block_sum(s2, sh);
-        out = amax * sqrt(s2);
-    }
-    if (threadIdx.x == 0) resid[c] = out;
+    res_final_body(V, Y, n, problem_type, lambda, b, scratch + (long long)c * VMB_MAXBLK * 4, nblk, c, resid, sh);
 }
 
 __host__ inline int vmb_blocks(int n) {
@@ -490,15 +525,16 @@ cudaError_t vec_gram(const cplx* V, int n, int C, cplx* G, cudaStream_t stream) 
     return cudaGetLastError();
 }
 
-size_t vec_scratch_doubles(long long C) { return (size_t)C * VMB_MAXBLK * 4; }
+// per-block partials [C][VMB_MAXBLK][4] + one block-done counter per candidate (must be zero-initialised once)
+size_t vec_scratch_doubles(long long C) { return (size_t)C * VMB_MAXBLK * 4 + (size_t)C; }
 
 cudaError_t vec_rq_finish(const cplx* V, const cplx* Y, int n, int C, cplx* lambda, double* vnorm2, int* status,
-                          double* scratch, cudaStream_t stream) {
+                          double* scratch, cudaStream_t stream, int scratch_cap) {
     if (C <= 0) return cudaSuccess;
     if (scratch && n >= VMB_MIN_N) {
         const int nblk = vmb_blocks(n);
-        rq_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, scratch);
-        rq_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(scratch, nblk, C, lambda, vnorm2, status);
+        rq_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, scratch, scratch_cap > 0 ? scratch_cap : 0, lambda, vnorm2, status);
+        if (scratch_cap <= 0) rq_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(scratch, nblk, C, lambda, vnorm2, status);
         return cudaGetLastError();
     }
     rq_finish_kernel<<<C, RED_NT, 0, stream>>>(V, Y, n, lambda, vnorm2, status);
@@ -520,12 +556,12 @@ cudaError_t vec_mix_normalise(cplx* V, const cplx* X, int n, int C, int problem_
 }
 
 cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda,
-                                const cplx* b, double* resid, double* scratch, cudaStream_t stream) {
+                                const cplx* b, double* resid, double* scratch, cudaStream_t stream, int scratch_cap) {
     if (C <= 0) return cudaSuccess;
     if (scratch && n >= VMB_MIN_N) {
         const int nblk = vmb_blocks(n);
-        res_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch);
-        res_final_kernel<<<C, RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch, nblk, resid);
+        res_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch, scratch_cap > 0 ? scratch_cap : 0, resid);
+        if (scratch_cap <= 0) res_final_kernel<<<C, RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch, nblk, resid);
         return cudaGetLastError();
     }
     residual_finish_kernel<<<C, RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, resid);
@@ -537,7 +573,7 @@ cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int 
 // its slice, the per-block partials in `scratch` are combined over the ranks, then the `final` / `apply` kernel runs ----
 int vec_part_blocks(long long n) { return vmb_blocks((int)n); }
 cudaError_t vec_rq_part(const cplx* V, const cplx* Y, int n, int C, double* scratch, int nblk, cudaStream_t stream) {
-    rq_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, scratch);
+    rq_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, scratch, 0, nullptr, nullptr, nullptr);
     return cudaGetLastError();
 }
 cudaError_t vec_rq_final(const double* scratch, int nblk, int C, cplx* lambda, double* vnorm2, int* status, cudaStream_t stream) {
@@ -557,7 +593,7 @@ cudaError_t vec_mix_apply(cplx* V, int n, int C, int problem_type, double* mixno
 }
 cudaError_t vec_res_part(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda, const cplx* b,
                          double* scratch, int nblk, cudaStream_t stream) {
-    res_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch);
+    res_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch, 0, nullptr);
     return cudaGetLastError();
 }
 cudaError_t vec_res_final(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda, const cplx* b,

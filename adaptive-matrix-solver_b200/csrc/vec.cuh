@@ -11,8 +11,10 @@ cudaError_t vec_rowmajor_to_colmajor(const cplx* in_rm, cplx* out_cm, int n, cud
 // `scratch` (vec_scratch_doubles(C) doubles, may be null): with it, vectors of n >= 32768 are reduced by many CTAs per
 // candidate (two-level, fixed-order partial sums) instead of one -- the n ~ 1e6 sparse configurations
 size_t vec_scratch_doubles(long long C);
+// scratch_cap > 0: the candidate capacity the scratch buffer was sized (and zero-initialised) for -- the block-done counters sit
+// behind the partials of that many candidates, and the last block of a candidate folds the final reduction into the same launch
 cudaError_t vec_rq_finish(const cplx* V, const cplx* Y, int n, int C, cplx* lambda, double* vnorm2, int* status,
-                          double* scratch, cudaStream_t stream);
+                          double* scratch, cudaStream_t stream, int scratch_cap = 0);
 
 // eigen : v <- (1-a) v + a x ; nv = ||v||_2 ; v /= nv when nv > 1e-10 else status MIX_COLLAPSED (v left unnormalised)
 // linear: v <- (1-a) v + a x ; nv = ||v||_2 (reported only)
@@ -22,7 +24,7 @@ cudaError_t vec_mix_normalise(cplx* V, const cplx* X, int n, int C, int problem_
 
 // eigen : r_c = || y_c - lambda_c v_c ||_2       linear: r_c = || y_c - b ||_2
 cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int problem_type, const cplx* lambda,
-                                const cplx* b, double* resid, double* scratch, cudaStream_t stream);
+                                const cplx* b, double* resid, double* scratch, cudaStream_t stream, int scratch_cap = 0);
 
 // Y[c] = A_rowmajor * V[c]: HBM-bound batched matvec, one warp per matrix row, CB candidates per pass
 cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
