@@ -70,17 +70,80 @@ __global__ void __launch_bounds__(256) lu_build_aug_kernel(cplx* W, long long st
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PANEL_MAXC = 8;
 
+// MAUS_PANEL_PROF (profiling build only, `make PROF=1`): per-phase clock64() sums of thread 0 of cluster rank 0 of candidate 0
+#ifdef MAUS_PANEL_PROF
+__device__ unsigned long long g_panel_prof[16];
+#define PP_DECL __shared__ long long pp_acc[16]; long long pp_last = 0; const bool pp_on = (blockIdx.x == 0 && threadIdx.x == 0); \
+    if (pp_on) { for (int i_ = 0; i_ < 16; ++i_) pp_acc[i_] = 0; pp_last = clock64(); }
+#define PP(i) do { if (pp_on) { long long t_ = clock64(); pp_acc[i] += t_ - pp_last; pp_last = t_; } } while (0)
+#define PP_FLUSH do { if (pp_on) { for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&g_panel_prof[i_], (unsigned long long)pp_acc[i_]); atomicAdd(&g_panel_prof[15], 1ULL); } } while (0)
+#else
+#define PP_DECL
+#define PP(i) do { } while (0)
+#define PP_FLUSH do { } while (0)
+#endif
+
+// One 16-byte-granular record per CTA and column: the CTA's best row, published into every CTA of the cluster.
 template <int IB>
-struct PanelSlot {
-    double val;        // izamax metric of the CTA's best row, -1 when the CTA has no live row
-    int row;           // panel-relative row index
+struct __align__(16) PanelSlot {
+    unsigned long long key;   // pivot key of the CTA's best live row (pivot_key below); 0 = the CTA has no live row
+    int row;                  // panel-relative row index
     int pad;
-    cplx recip;        // 1 / pivot
-    cplx data[IB];     // that row's inner-block entries
+    cplx recip;               // 1 / pivot
+    cplx data[IB];            // that row's window (columns j .. j + IB - 1 of the inner block)
 };
 
+// Pivot order without FP64 compares: |re| + |im| >= +0 (NaN mapped to +inf), and non-negative doubles order like their bit
+// patterns.  key = bits + 1 so that 0 means "no live row"; key == 1 is an exact zero pivot.
+__device__ __forceinline__ unsigned long long pivot_key(cplx a) {
+    double v = cabs1(a);
+    if (v != v) v = INFINITY;
+    return (unsigned long long)__double_as_longlong(v) + 1ULL;
+}
+// warp-wide (max key, then min row) with three REDUX instead of five dependent shuffle rounds of 64-bit values
+__device__ __forceinline__ void warp_best(unsigned long long& key, int& row) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    bool c = hi == mh;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, c ? lo : 0u);
+    c = c && lo == ml;
+    const unsigned mr = __reduce_min_sync(0xffffffffu, c ? (unsigned)row : 0x7fffffffu);
+    key = ((unsigned long long)mh << 32) | ml; row = (int)mr;
+}
+__device__ __forceinline__ uint32_t pn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t pn_mapa(uint32_t addr, int cta) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta)); return r;
+}
+// 16-byte store into a peer CTA's shared memory that also counts 16 bytes on the peer's mbarrier (SASS STAS.128): data and
+// "it has arrived" travel together, no separate flag or fence
+__device__ __forceinline__ void pn_st_async16(uint32_t dst, double2 v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+                 ::"r"(dst), "d"(v.x), "d"(v.y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void pn_bar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t a = pn_smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+
 // MINB = CTAs per SM the register allocation is held to, UW = columns per step of the in-leaf rank-IB update (the update keeps
-// 2 UW columns of prefetch + UW in flight per row: UW = 4 needs ~128 registers, UW = 2 fits 64)
+// 2 UW columns of prefetch + UW in flight per row: UW = 4 needs ~128 registers)
+//
+// Column step (the kernel is bound by the LATENCY of this chain, 2 x jb x panels times per factorisation; round-2 clocks:
+// 4 900 cycles per column with shuffle reductions on doubles, a serial slot scan and cg::cluster.sync):
+//   thread best -> warp_best (REDUX) -> smem -> CTA barrier -> warp_best over the warps' results
+//   -> the owner warp sends the CTA's record (key, row, 1/pivot, window) to EVERY CTA of the cluster with st.async, which
+//      completes transaction bytes on the receiver's mbarrier: the exchange is the synchronisation, there is no cluster
+//      barrier in the column loop; records and mbarriers are double-buffered by column parity
+//   -> wait on the own mbarrier -> warp_best over the <= 8 records -> scale, park the multiplier in shared memory (lbuf),
+//      rank-1 update of the register window.
 template <int R, int IB, int PANEL_NT, int MINB, int UW>
 __global__ void __launch_bounds__(PANEL_NT, MINB)
 lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pairs, int* info) {
@@ -93,16 +156,29 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
     const int m = n - k0;
     const int ld = n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = PANEL_NT / 32;
+    constexpr int S16 = (int)(sizeof(PanelSlot<IB>) / 16);     // 16-byte pieces of a record
+    static_assert(NW <= 32 && PANEL_MAXC <= 32, "second-level reductions run inside one warp");
     cplx* P = W + (long long)b * strideW + (long long)k0 * ld + k0;   // P[r + c*ld]
 
+    extern __shared__ __align__(16) unsigned char panel_dyn[];
+    cplx* lbuf = reinterpret_cast<cplx*>(panel_dyn);          // multipliers of the current inner block: [R][IB][PANEL_NT]
     __shared__ PanelSlot<IB> slots[2][PANEL_MAXC];
-    __shared__ double wval[PANEL_NT / 32];
-    __shared__ int wrow[PANEL_NT / 32];
+    __shared__ PanelSlot<IB> pub;                             // owner lane -> owner warp
+    __shared__ __align__(8) uint64_t xbar[2];
+    __shared__ unsigned long long wkey[2][NW];
+    __shared__ int wrow[2][NW];
     __shared__ cplx L11[IB][IB + 1];
     __shared__ cplx U12[IB][LU_NB];
     __shared__ int piv[LU_NB];
     __shared__ unsigned char is_piv[LU_NB];
-    __shared__ cplx pub[IB + 1];           // owner lane -> owner warp: the pivot row's window and 1/pivot
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pn_smem_u32(&xbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pn_smem_u32(&xbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();      // every CTA's mbarriers exist before the first remote transaction can arrive
 
     int row[R];
     bool valid[R], done[R];
@@ -110,6 +186,7 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
     for (int q = 0; q < R; ++q) { row[q] = tg + q * T; valid[q] = row[q] < m; done[q] = false; }
     bool zero_seen = false;
     int zero_col = 0;
+    PP_DECL
 
     for (int ib0 = 0; ib0 < jb; ib0 += IB) {
         const int ibw = min(IB, jb - ib0);
@@ -124,81 +201,76 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
             for (int i = 0; i < IB; ++i)
                 a[q][i] = (live && i < ibw) ? P[row[q] + (long long)(ib0 + i) * ld] : cmake(0.0, 0.0);
         }
+        PP(0);
 #pragma unroll 1
         for (int j = 0; j < ibw; ++j) {
-            // ---- pivot search: thread -> warp -> CTA -> cluster ----
-            double bv = -1.0; int br = 0x7fffffff;
+            const int col = ib0 + j, buf = col & 1;
+            const uint32_t par = (uint32_t)((col >> 1) & 1);
+            // ---- pivot search: thread -> warp -> CTA ----
+            unsigned long long key = 0ULL; int br = 0x7fffffff;
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 if (valid[q] && !done[q]) {
-                    double v = cabs1(a[q][0]);
-                    if (v != v) v = INFINITY;
-                    if (v > bv || (v == bv && row[q] < br)) { bv = v; br = row[q]; }
+                    const unsigned long long kq = pivot_key(a[q][0]);
+                    if (kq > key || (kq == key && row[q] < br)) { key = kq; br = row[q]; }
                 }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                int orow = __shfl_xor_sync(0xffffffffu, br, o);
-                if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; }
-            }
-            if (lane == 0) { wval[warp] = bv; wrow[warp] = br; }
+            warp_best(key, br);
+            if (lane == 0) { wkey[buf][warp] = key; wrow[buf][warp] = br; }
+            // this column's transactions: one record from every CTA of the cluster (armed before anybody can wait on it)
+            if (threadIdx.x == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             ::"r"(pn_smem_u32(&xbar[buf])), "r"((uint32_t)(NC * sizeof(PanelSlot<IB>))) : "memory");
             __syncthreads();
-            double cv = -1.0; int cr = 0x7fffffff;
-#pragma unroll
-            for (int w = 0; w < PANEL_NT / 32; ++w) {
-                double ov = wval[w]; int orow = wrow[w];
-                if (ov > cv || (ov == cv && orow < cr)) { cv = ov; cr = orow; }
-            }
-            // the warp that owns the CTA's best row publishes it into every CTA's slot[rank]: the owner lane broadcasts
-            // its window by shuffles, then the 32 lanes spread the remote (DSMEM) stores
-            if (cv >= 0.0) {
-                const int owner_t = (cr % T) - rank * PANEL_NT;      // thread of this CTA that holds row cr
-                const int owner_q = cr / T;
+            PP(1);
+            unsigned long long ck = (lane < NW) ? wkey[buf][lane] : 0ULL;
+            int cr = (lane < NW) ? wrow[buf][lane] : 0x7fffffff;
+            warp_best(ck, cr);
+            // ---- the warp that owns the CTA's best row (warp 0 when the CTA has no live row) sends the record ----
+            {
+                const bool have = ck != 0ULL;
+                const int owner_t = have ? (cr % T) - rank * PANEL_NT : 0;      // thread of this CTA that holds row cr
+                const int owner_q = have ? cr / T : 0;
                 if (warp == (owner_t >> 5)) {
-                    // the owner lane parks its window + 1/pivot in CTA-local shared memory (one hop instead of a chain of
-                    // 2 IB dependent shuffles), then the 32 lanes spread the remote (DSMEM) stores
-                    const int ol = owner_t & 31;
-                    if (lane == ol) {
+                    if (lane == (owner_t & 31)) {
+                        pub.key = ck; pub.row = cr; pub.pad = 0;
 #pragma unroll
                         for (int i = 0; i < IB; ++i) {
                             cplx sel = a[0][i];
 #pragma unroll
                             for (int q = 1; q < R; ++q) if (owner_q == q) sel = a[q][i];
-                            pub[i] = sel;
-                            if (i == 0) pub[IB] = crecip(sel);
+                            pub.data[i] = sel;
+                            if (i == 0) pub.recip = have ? crecip(sel) : cmake(0.0, 0.0);
                         }
                     }
                     __syncwarp();
-                    const int e = lane % IB;
-                    const cplx keep = pub[e], rc = pub[IB];
-                    for (int d = lane / IB; d < NC; d += 32 / IB) {
-                        PanelSlot<IB>* s = cluster.map_shared_rank(&slots[j & 1][rank], d);
-                        s->data[e] = keep;
-                        if (e == 0) { s->val = cv; s->row = cr; s->recip = rc; }
+                    const double2* src = reinterpret_cast<const double2*>(&pub);
+                    const uint32_t slot0 = pn_smem_u32(&slots[buf][rank]), bar0 = pn_smem_u32(&xbar[buf]);
+                    for (int idx = lane; idx < NC * S16; idx += 32) {
+                        const int d = idx / S16, e = idx - d * S16;
+                        pn_st_async16(pn_mapa(slot0 + 16u * (uint32_t)e, d), src[e], pn_mapa(bar0, d));
                     }
-                    __syncwarp();          // pub is rewritten by the next column's owner only after the cluster barrier, but keep the warp together
-                }
-            } else if (threadIdx.x == 0) {
-                for (int d = 0; d < NC; ++d) {
-                    PanelSlot<IB>* s = cluster.map_shared_rank(&slots[j & 1][rank], d);
-                    s->val = -1.0; s->row = 0x7fffffff;
+                    // pub is rewritten by the next column's owner after the next CTA barrier, which this warp reaches
+                    // only after the loads above have returned
                 }
             }
-            cluster.sync();
-            double wv = -1.0; int wr = 0x7fffffff, wi = 0;
-            for (int d = 0; d < NC; ++d) {
-                double ov = slots[j & 1][d].val; int orow = slots[j & 1][d].row;
-                if (ov > wv || (ov == wv && orow < wr)) { wv = ov; wr = orow; wi = d; }
-            }
-            const PanelSlot<IB>& ws = slots[j & 1][wi];
-            if (threadIdx.x == 0) piv[ib0 + j] = wr;
-            const bool zero = !(wv > 0.0);
-            if (zero && !zero_seen) { zero_seen = true; zero_col = k0 + ib0 + j + 1; }
+            PP(2);
+            pn_bar_wait(&xbar[buf], par);
+            PP(3);
+            unsigned long long wk = (lane < NC) ? slots[buf][lane].key : 0ULL;
+            int wr = (lane < NC) ? slots[buf][lane].row : 0x7fffffff;
+            const unsigned long long myk = wk; const int myr = wr;
+            warp_best(wk, wr);
+            const unsigned hit = __ballot_sync(0xffffffffu, lane < NC && myk == wk && myr == wr);
+            const int wi = hit ? (__ffs(hit) - 1) : 0;
+            const PanelSlot<IB>& ws = slots[buf][wi];
+            if (threadIdx.x == 0) piv[col] = wr;
+            const bool zero = wk <= 1ULL;                                 // no live row at all, or the best |a| is exactly 0
+            if (zero && !zero_seen) { zero_seen = true; zero_col = k0 + col + 1; }
             const cplx rc = ws.recip;
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 if (valid[q] && !done[q]) {
-                    cplx* prow = P + row[q] + (long long)(ib0 + j) * ld;
+                    cplx* prow = P + row[q] + (long long)col * ld;
                     if (row[q] == wr) {
                         done[q] = true;                               // my window holds U(j, j..): final values
 #pragma unroll
@@ -208,11 +280,13 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
                         cplx l = zero ? a[q][0] : cmul(a[q][0], rc);
                         prow[0] = l;                                   // multiplier, stays in its physical row
                         if (zero) l = cmake(0.0, 0.0);
+                        lbuf[(q * IB + j) * PANEL_NT + threadIdx.x] = l;   // ... and a copy for the block update below
 #pragma unroll
                         for (int i = 0; i + 1 < IB; ++i) { cplx x = a[q][i + 1]; cfms(x, l, ws.data[i + 1]); a[q][i] = x; }
                         a[q][IB - 1] = cmake(0.0, 0.0);
                     }
                 }
+            PP(4);
         }
         const int rest = jb - (ib0 + ibw);
         if (rest > 0) {
@@ -223,29 +297,42 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
                 if (i < jj && jj < ibw) L11[jj][i] = __ldcg(&P[piv[ib0 + jj] + (long long)(ib0 + i) * ld]);
             }
             __syncthreads();
-            // (i) U12 block = L11^-1 * (pivot rows, remaining panel columns); every CTA computes its own copy
+            PP(5);
+            // (i) U12 block = L11^-1 * (pivot rows, remaining panel columns); every CTA computes its own copy.  All loads of
+            // a column are issued before the first dependent FMA (one L2 round trip instead of ibw)
             if ((int)threadIdx.x < rest) {
                 const int c = threadIdx.x;
                 const long long coff = (long long)(ib0 + ibw + c) * ld;
-                for (int j = 0; j < ibw; ++j) {
-                    cplx x = __ldcg(&P[piv[ib0 + j] + coff]);
-                    for (int i = 0; i < j; ++i) cfms(x, L11[j][i], U12[i][c]);
-                    U12[j][c] = x;
+                cplx xs[IB];
+#pragma unroll
+                for (int j = 0; j < IB; ++j) xs[j] = (j < ibw) ? __ldcg(&P[piv[ib0 + j] + coff]) : cmake(0.0, 0.0);
+#pragma unroll
+                for (int j = 0; j < IB; ++j) {
+                    if (j < ibw) {
+                        cplx x = xs[j];
+#pragma unroll
+                        for (int i = 0; i < j; ++i) cfms(x, L11[j][i], xs[i]);
+                        xs[j] = x;
+                        U12[j][c] = x;
+                    }
                 }
             }
+            PP(6);
             cluster.sync();   // every CTA has read the pivot rows before rank 0 overwrites them with U12
+            PP(7);
             if (rank == 0 && (int)threadIdx.x < rest) {
                 const long long coff = (long long)(ib0 + ibw + threadIdx.x) * ld;
                 for (int j = 0; j < ibw; ++j) P[piv[ib0 + j] + coff] = U12[j][threadIdx.x];
             }
-            // (ii) rank-ibw update of the remaining panel columns for the rows that are still live: four columns at a
-            // time (independent FMA chains), the next four prefetched while the current ones are updated
+            // (ii) rank-ibw update of the remaining panel columns for the rows that are still live: UW columns at a
+            // time (independent FMA chains), the next ones prefetched while the current ones are updated; the multipliers
+            // come from shared memory (lbuf), not from the copy in global memory
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 if (valid[q] && !done[q]) {
                     cplx l[IB];
 #pragma unroll
-                    for (int j = 0; j < IB; ++j) l[j] = (j < ibw) ? P[row[q] + (long long)(ib0 + j) * ld] : cmake(0.0, 0.0);
+                    for (int j = 0; j < IB; ++j) l[j] = (j < ibw) ? lbuf[(q * IB + j) * PANEL_NT + threadIdx.x] : cmake(0.0, 0.0);
                     cplx* prow = P + row[q] + (long long)(ib0 + ibw) * ld;
                     const int rest4 = (rest / UW) * UW;
                     // software pipeline two groups of UW columns deep (three measured no better): the loads of columns c + UW .. c + 3 UW - 1
@@ -280,12 +367,14 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
                         prow[(long long)c * ld] = x;
                     }
                 }
-            // Updates written in (ii) are read by other CTAs in the next block's step (i): the column loop of the next
-            // block contains cluster barriers (release/acquire) before that read, and the reads use ld.cg.
+            // Updates written in (ii) are read by other CTAs in the next block's step (i): the cluster barrier at the top of
+            // that step (release / acquire) orders them, and the reads use ld.cg.
             __syncthreads();   // U12 / L11 are rewritten by the next block
+            PP(8);
         }
     }
     __syncthreads();
+    PP_FLUSH;
     // ---- net row permutation of this panel (relative to k0) ----
     if (rank == 0) {
         if (threadIdx.x < LU_NB) is_piv[threadIdx.x] = 0;
@@ -519,6 +608,14 @@ __global__ void __launch_bounds__(BS_NT) lu_backsolve_kernel(const cplx* __restr
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
+#ifdef MAUS_PANEL_PROF
+extern "C" int maus_debug_panel_prof(unsigned long long* out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, g_panel_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(g_panel_prof, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#endif
+
 cudaError_t lu_build_aug(cplx* W, long long strideW, int n, int batch, const cplx* Acm, const cplx* sigma,
                          const double* psi, const unsigned long long* keys, const cplx* R_cm, const cplx* rhs,
                          long long rhs_stride, cudaStream_t stream, int conj_in) {
@@ -535,7 +632,14 @@ static cudaError_t launch_panel(cplx* W, long long strideW, int n, int k0, int j
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(batch * nc, 1, 1);
     cfg.blockDim = dim3(PANEL_NT, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    const size_t dyn = (size_t)R * IB * PANEL_NT * sizeof(cplx);       // lbuf
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(lu_panel_kernel<R, IB, PANEL_NT, MINB, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cfg.dynamicSmemBytes = dyn;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
