@@ -100,6 +100,18 @@ __device__ __forceinline__ unsigned long long pivot_key(cplx a) {
     if (v != v) v = INFINITY;
     return (unsigned long long)__double_as_longlong(v) + 1ULL;
 }
+// 1 / a with ONE division (Smith's formula in crecip costs three dependent FP64 divisions, ~440 cycles on the owner's critical
+// path of every column; this one ~200): scale by an exact power of two so that |a|^2 can neither overflow nor underflow,
+// then conj(a') / |a'|^2.  Exponent fields 0 (zero / subnormal) and 2047 (inf / nan) take the robust path.
+__device__ __forceinline__ cplx pivot_recip(cplx a) {
+    const double mx = fmax(fabs(a.x), fabs(a.y));
+    const int e = (int)((__double_as_longlong(mx) >> 52) & 0x7ff);
+    if (e == 0 || e >= 2046) return crecip(a);
+    const double sc = __longlong_as_double((long long)(2046 - e) << 52);       // 2^(1023 - e): max(|x'|, |y'|) in [1, 2)
+    const double xs = a.x * sc, ys = a.y * sc;
+    const double inv = 1.0 / fma(xs, xs, ys * ys);
+    return cmake((xs * inv) * sc, (-ys * inv) * sc);
+}
 // warp-wide (max key, then min row) with three REDUX instead of five dependent shuffle rounds of 64-bit values
 __device__ __forceinline__ void warp_best(unsigned long long& key, int& row) {
     const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
@@ -206,16 +218,20 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
         for (int j = 0; j < ibw; ++j) {
             const int col = ib0 + j, buf = col & 1;
             const uint32_t par = (uint32_t)((col >> 1) & 1);
-            // ---- pivot search: thread -> warp -> CTA ----
-            unsigned long long key = 0ULL; int br = 0x7fffffff;
+            // ---- pivot search: thread -> warp -> CTA.  The "row" that travels through the min-reductions carries its owner in
+            // the low bits (row << 2 | q inside a warp, then << 5 | warp inside the CTA, row << 4 | CTA rank in the cluster):
+            // rows are unique, so the order is the row order, and nobody has to divide by the cluster's thread count ----
+            unsigned long long key = 0ULL; int myw = 0x7fffffff;
 #pragma unroll
             for (int q = 0; q < R; ++q)
                 if (valid[q] && !done[q]) {
                     const unsigned long long kq = pivot_key(a[q][0]);
-                    if (kq > key || (kq == key && row[q] < br)) { key = kq; br = row[q]; }
+                    const int wq = (row[q] << 2) | q;
+                    if (kq > key || (kq == key && wq < myw)) { key = kq; myw = wq; }
                 }
-            warp_best(key, br);
-            if (lane == 0) { wkey[buf][warp] = key; wrow[buf][warp] = br; }
+            int bw = myw;
+            warp_best(key, bw);
+            if (lane == 0) { wkey[buf][warp] = key; wrow[buf][warp] = (key != 0ULL) ? ((bw << 5) | warp) : 0x7fffffff; }
             // this column's transactions: one record from every CTA of the cluster (armed before anybody can wait on it)
             if (threadIdx.x == 0)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
@@ -223,23 +239,24 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
             __syncthreads();
             PP(1);
             unsigned long long ck = (lane < NW) ? wkey[buf][lane] : 0ULL;
-            int cr = (lane < NW) ? wrow[buf][lane] : 0x7fffffff;
-            warp_best(ck, cr);
+            int cw = (lane < NW) ? wrow[buf][lane] : 0x7fffffff;
+            warp_best(ck, cw);
             // ---- the warp that owns the CTA's best row (warp 0 when the CTA has no live row) sends the record ----
             {
                 const bool have = ck != 0ULL;
-                const int owner_t = have ? (cr % T) - rank * PANEL_NT : 0;      // thread of this CTA that holds row cr
-                const int owner_q = have ? cr / T : 0;
-                if (warp == (owner_t >> 5)) {
-                    if (lane == (owner_t & 31)) {
-                        pub.key = ck; pub.row = cr; pub.pad = 0;
+                const int owner_warp = have ? (cw & 31) : 0;
+                if (warp == owner_warp) {
+                    const int ow = cw >> 5;                              // (row << 2) | q of the CTA's best row
+                    if (have ? (myw == ow) : (lane == 0)) {
+                        const int owner_q = have ? (ow & 3) : 0;
+                        pub.key = ck; pub.row = have ? (((ow >> 2) << 4) | rank) : 0x7fffffff; pub.pad = 0;
 #pragma unroll
                         for (int i = 0; i < IB; ++i) {
                             cplx sel = a[0][i];
 #pragma unroll
                             for (int q = 1; q < R; ++q) if (owner_q == q) sel = a[q][i];
                             pub.data[i] = sel;
-                            if (i == 0) pub.recip = have ? crecip(sel) : cmake(0.0, 0.0);
+                            if (i == 0) pub.recip = have ? pivot_recip(sel) : cmake(0.0, 0.0);
                         }
                     }
                     __syncwarp();
@@ -257,11 +274,10 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
             pn_bar_wait(&xbar[buf], par);
             PP(3);
             unsigned long long wk = (lane < NC) ? slots[buf][lane].key : 0ULL;
-            int wr = (lane < NC) ? slots[buf][lane].row : 0x7fffffff;
-            const unsigned long long myk = wk; const int myr = wr;
-            warp_best(wk, wr);
-            const unsigned hit = __ballot_sync(0xffffffffu, lane < NC && myk == wk && myr == wr);
-            const int wi = hit ? (__ffs(hit) - 1) : 0;
+            int ww = (lane < NC) ? slots[buf][lane].row : 0x7fffffff;
+            warp_best(wk, ww);
+            const int wi = (wk != 0ULL) ? (ww & 15) : 0;                 // CTA whose record won
+            const int wr = (wk != 0ULL) ? (ww >> 4) : 0x7fffffff;        // the pivot row
             const PanelSlot<IB>& ws = slots[buf][wi];
             if (threadIdx.x == 0) piv[col] = wr;
             const bool zero = wk <= 1ULL;                                 // no live row at all, or the best |a| is exactly 0
@@ -324,49 +340,78 @@ lu_panel_kernel(cplx* W, long long strideW, int n, int k0, int jb, LuPairs* pair
                 const long long coff = (long long)(ib0 + ibw + threadIdx.x) * ld;
                 for (int j = 0; j < ibw; ++j) P[piv[ib0 + j] + coff] = U12[j][threadIdx.x];
             }
-            // (ii) rank-ibw update of the remaining panel columns for the rows that are still live: UW columns at a
-            // time (independent FMA chains), the next ones prefetched while the current ones are updated; the multipliers
-            // come from shared memory (lbuf), not from the copy in global memory
+            // (ii) rank-ibw update of the remaining panel columns for the rows that are still live.  The R rows of a thread
+            // go through the loop TOGETHER, UW columns at a time: R * UW * 2 independent FMA chains (a DFMA result is ready
+            // after ~21 cycles) and every U12 entry fetched from shared memory serves R rows; the multipliers are read from
+            // lbuf as they are needed instead of occupying 4 IB registers per row; the next UW columns of every row are
+            // prefetched while the current ones are updated (PFD groups deep: the rows come from L2 / HBM, ~1 us away)
+            {
+                constexpr int PFD = (R == 1) ? 2 : 1;
+                bool lv[R];
+                cplx* prow[R];
 #pragma unroll
-            for (int q = 0; q < R; ++q)
-                if (valid[q] && !done[q]) {
-                    cplx l[IB];
-#pragma unroll
-                    for (int j = 0; j < IB; ++j) l[j] = (j < ibw) ? lbuf[(q * IB + j) * PANEL_NT + threadIdx.x] : cmake(0.0, 0.0);
-                    cplx* prow = P + row[q] + (long long)(ib0 + ibw) * ld;
-                    const int rest4 = (rest / UW) * UW;
-                    // software pipeline two groups of UW columns deep (three measured no better): the loads of columns c + UW .. c + 3 UW - 1
-                    // are in flight while columns c .. c + UW - 1 are updated (the rows come from L2 / HBM, ~1 us away)
-                    cplx n0[UW], n1[UW];
-#pragma unroll
-                    for (int u = 0; u < UW; ++u) {
-                        n0[u] = (rest4 > 0) ? prow[(long long)u * ld] : cmake(0.0, 0.0);
-                        n1[u] = (rest4 > UW) ? prow[(long long)(UW + u) * ld] : cmake(0.0, 0.0);
-                    }
-#pragma unroll 1
-                    for (int c = 0; c < rest4; c += UW) {
-                        cplx x[UW];
-#pragma unroll
-                        for (int u = 0; u < UW; ++u) { x[u] = n0[u]; n0[u] = n1[u]; }
-                        if (c + 2 * UW < rest4) {
-#pragma unroll
-                            for (int u = 0; u < UW; ++u) n1[u] = prow[(long long)(c + 2 * UW + u) * ld];
-                        }
-#pragma unroll
-                        for (int j = 0; j < IB; ++j) {
-#pragma unroll
-                            for (int u = 0; u < UW; ++u) cfms(x[u], l[j], U12[j][c + u]);
-                        }
-#pragma unroll
-                        for (int u = 0; u < UW; ++u) prow[(long long)(c + u) * ld] = x[u];
-                    }
-                    for (int c = rest4; c < rest; ++c) {
-                        cplx x = prow[(long long)c * ld];
-#pragma unroll
-                        for (int j = 0; j < IB; ++j) cfms(x, l[j], U12[j][c]);
-                        prow[(long long)c * ld] = x;
-                    }
+                for (int q = 0; q < R; ++q) {
+                    lv[q] = valid[q] && !done[q];
+                    prow[q] = P + row[q] + (long long)(ib0 + ibw) * ld;
+                    if (ibw < IB)      // ragged last block: the multipliers of the missing columns are zero
+                        for (int j = ibw; j < IB; ++j) lbuf[(q * IB + j) * PANEL_NT + threadIdx.x] = cmake(0.0, 0.0);
                 }
+                const int rest4 = (rest / UW) * UW;
+                cplx nx[PFD][R][UW];
+#pragma unroll
+                for (int d = 0; d < PFD; ++d)
+#pragma unroll
+                    for (int q = 0; q < R; ++q)
+#pragma unroll
+                        for (int u = 0; u < UW; ++u)
+                            nx[d][q][u] = (lv[q] && d * UW < rest4) ? prow[q][(long long)(d * UW + u) * ld] : cmake(0.0, 0.0);
+#pragma unroll 1
+                for (int c = 0; c < rest4; c += UW) {
+                    cplx x[R][UW];
+#pragma unroll
+                    for (int q = 0; q < R; ++q)
+#pragma unroll
+                        for (int u = 0; u < UW; ++u) {
+                            x[q][u] = nx[0][q][u];
+#pragma unroll
+                            for (int d = 0; d + 1 < PFD; ++d) nx[d][q][u] = nx[d + 1][q][u];
+                        }
+                    if (c + PFD * UW < rest4) {
+#pragma unroll
+                        for (int q = 0; q < R; ++q)
+#pragma unroll
+                            for (int u = 0; u < UW; ++u)
+                                if (lv[q]) nx[PFD - 1][q][u] = prow[q][(long long)(c + PFD * UW + u) * ld];
+                    }
+#pragma unroll
+                    for (int j = 0; j < IB; ++j) {
+                        cplx uj[UW];
+#pragma unroll
+                        for (int u = 0; u < UW; ++u) uj[u] = U12[j][c + u];
+#pragma unroll
+                        for (int q = 0; q < R; ++q) {
+                            const cplx lj = lbuf[(q * IB + j) * PANEL_NT + threadIdx.x];
+#pragma unroll
+                            for (int u = 0; u < UW; ++u) cfms(x[q][u], lj, uj[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < R; ++q)
+                        if (lv[q]) {
+#pragma unroll
+                            for (int u = 0; u < UW; ++u) prow[q][(long long)(c + u) * ld] = x[q][u];
+                        }
+                }
+                for (int c = rest4; c < rest; ++c)
+#pragma unroll
+                    for (int q = 0; q < R; ++q)
+                        if (lv[q]) {
+                            cplx x = prow[q][(long long)c * ld];
+#pragma unroll
+                            for (int j = 0; j < IB; ++j) cfms(x, lbuf[(q * IB + j) * PANEL_NT + threadIdx.x], U12[j][c]);
+                            prow[q][(long long)c * ld] = x;
+                        }
+            }
             // Updates written in (ii) are read by other CTAs in the next block's step (i): the cluster barrier at the top of
             // that step (release / acquire) orders them, and the reads use ld.cg.
             __syncthreads();   // U12 / L11 are rewritten by the next block
@@ -659,15 +704,13 @@ cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batc
     if (force_r < 0) { const char* e = getenv("MAUS_PANEL_R"); force_r = e ? atoi(e) : 0; }
     // configurations (rows per cluster = NC * NT * R, NC <= 8):
     //   A: NT 512, R 1, IB 16 -> <= 4096 rows, lowest latency (small batches)
-    //   B: NT 256, R 2, IB 8  -> <= 4096 rows, two CTAs of different clusters share an SM so one cluster's barrier
+    //   B: NT 256, R 2, IB 8  -> <= 4096 rows, two CTAs of different clusters share an SM so one cluster's exchange
     //                            latency hides behind the other's arithmetic (large batches are SM-time bound)
     //   C: NT 512, R 2, IB 8  -> <= 8192 rows
-    //   D: NT 512, R 1, IB 8, 64 registers -> <= 4096 rows, two 512-thread CTAs per SM: the same rows per SM as B with twice
-    //                            the warps (32 per SM), half the serial work per thread and column
-    //   E: NT 256, R 2, IB 8, 80 registers -> three CTAs per SM
+    // (round 2 also measured 512 x 1 rows at 64 registers and 256 x 2 at 80 registers / three CTAs per SM: 82.7 / 65.7 ms
+    // against 55.9 ms for B at 128 candidates -- spills; removed)
     int mode = (batch >= 12) ? 1 : 0;
     if (force_r == 1) mode = 0; else if (force_r == 2) mode = 2; else if (force_r == 3) mode = 1;
-    else if (force_r == 4) mode = 3; else if (force_r == 5) mode = 4;
     if (m > PANEL_MAXC * 512) mode = 2;
     const int rows_per_cta = (mode == 2) ? 1024 : 512;
     // cluster size = exactly the CTAs the panel's rows need (1..8, not rounded up to a power of two: a CTA without rows
@@ -679,8 +722,6 @@ cudaError_t lu_panel(cplx* W, long long strideW, int n, int k0, int jb, int batc
     if (pow2) { nc = 1; while (nc < need) nc <<= 1; }
     if (mode == 0) return launch_panel<1, 16, 512, 1, 4>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
     if (mode == 1) return launch_panel<2, 8, 256, 2, 4>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
-    if (mode == 3) return launch_panel<1, 8, 512, 2, 2>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
-    if (mode == 4) return launch_panel<2, 8, 256, 3, 2>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
     return launch_panel<2, 8, 512, 1, 4>(W, strideW, n, k0, jb, batch, pairs, info, nc, stream);
 }
 
