@@ -132,6 +132,8 @@ __device__ __forceinline__ void pn_st_async16(uint32_t dst, double2 v, uint32_t 
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
                  ::"r"(dst), "d"(v.x), "d"(v.y), "r"(bar) : "memory");
 }
+// default semantics (acquire at CTA scope) as in every TMA / cluster-barrier consumer: the records arrive in THIS CTA's shared
+// memory through the barrier's own transaction count; acquire.cluster would add an L1 invalidation (CCTL.IVALL) per column
 __device__ __forceinline__ void pn_bar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     const uint32_t a = pn_smem_u32(bar);
@@ -139,7 +141,7 @@ __device__ __forceinline__ void pn_bar_wait(uint64_t* bar, uint32_t parity) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
     } while (!done);
