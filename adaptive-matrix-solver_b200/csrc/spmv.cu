@@ -150,6 +150,72 @@ __global__ void __launch_bounds__(SP_NT, MINB) csr_spmm_packed_kernel(const long
     }
 }
 
+// Eight candidates per pass: P[j][8], one matrix entry gathers one whole 128-byte line, fetched by 8 neighbouring lanes.  A warp
+// instruction then covers 4 entries with 4 fully used lines (the 4-candidate layout: 8 entries, 8 half lines -- the kernel is bound
+// by L1 wavefronts and L2 sectors per gathered byte, not by DRAM), and the matrix is streamed once per 8 candidates.  One warp walks
+// one row at a time: lane = 8 * s + c, s = 0..3.  Lane s keeps TWO accumulators, for the entries = s and = s + 4 (mod 8), adds them
+// and then runs the xor tree over s: exactly the association of the 8-lane kernels (whose first tree step adds lanes k and k ^ 4),
+// so the results stay bit-identical to csr_spmm_kernel.  Rows are walked grid-strided and software-pipelined like above.
+template <int SP_U, int MINB>
+__global__ void __launch_bounds__(SP_NT, MINB) csr_spmm_packed8_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                                 const cplx* __restrict__ vals, const cplx* __restrict__ P,
+                                                                 long long p_gstride, cplx* __restrict__ Y, long long ldy,
+                                                                 long long n, int c0, int ctotal) {
+    constexpr int CB = 8, SUBS = 4, NE = 2 * SP_U;         // NE entries per lane and chunk: u even -> residue s, u odd -> residue s + 4
+    constexpr int GPB = SP_NT / 32;                        // rows in flight per CTA
+    P += (long long)blockIdx.y * p_gstride;
+    c0 += (int)blockIdx.y * CB;
+    const int ncand = min(CB, ctotal - c0);
+    const int lane = threadIdx.x & 31, s = lane >> 3, c = lane & 7;
+    const long long stride = (long long)gridDim.x * GPB;
+    long long row = (long long)blockIdx.x * GPB + (threadIdx.x >> 5);
+    auto load_entries = [&](long long k0, long long k1, cplx* a, int* j) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const long long k = k0 + s + e * SUBS;          // e = 2u: residue s, e = 2u + 1: residue s + 4 (mod 8)
+            const bool ok = k < k1;
+            a[e] = ok ? __ldcs(&vals[k]) : cmake(0.0, 0.0);
+            j[e] = ok ? __ldcs(&colidx[k]) : -1;
+        }
+    };
+    long long k0 = 0, k1 = 0, k0n = 0, k1n = 0;
+    cplx an[NE]; int jn[NE];
+    if (row < n) { k0 = rowptr[row]; k1 = rowptr[row + 1]; }
+    load_entries(k0, k1, an, jn);
+    long long rown = row + stride;
+    if (rown < n) { k0n = rowptr[rown]; k1n = rowptr[rown + 1]; }
+    while (row < n) {                                       // warp-uniform: the whole warp works on one row
+        cplx a[NE]; int j[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { a[e] = an[e]; j[e] = jn[e]; }
+        cplx v[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) v[e] = (j[e] >= 0) ? __ldg(&P[(long long)j[e] * CB + c]) : cmake(0.0, 0.0);
+        const long long kc0 = k0, kc1 = k1, rown2 = rown + stride;
+        long long k0nn = 0, k1nn = 0;
+        load_entries(k0n, k1n, an, jn);
+        if (rown2 < n) { k0nn = rowptr[rown2]; k1nn = rowptr[rown2 + 1]; }
+        cplx acc0 = cmake(0.0, 0.0), acc1 = cmake(0.0, 0.0);
+#pragma unroll
+        for (int e = 0; e < NE; e += 2) { cfma(acc0, a[e], v[e]); cfma(acc1, a[e + 1], v[e + 1]); }
+        for (long long kb = kc0 + SUBS * NE; kb < kc1; kb += SUBS * NE) {
+            load_entries(kb, kc1, a, j);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) v[e] = (j[e] >= 0) ? __ldg(&P[(long long)j[e] * CB + c]) : cmake(0.0, 0.0);
+#pragma unroll
+            for (int e = 0; e < NE; e += 2) { cfma(acc0, a[e], v[e]); cfma(acc1, a[e + 1], v[e + 1]); }
+        }
+        cplx acc = cmake(acc0.x + acc1.x, acc0.y + acc1.y);
+#pragma unroll
+        for (int o = SUBS / 2; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o * CB);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o * CB);
+        }
+        if (s == 0 && c < ncand) Y[(long long)(c0 + c) * ldy + row] = acc;
+        row = rown; rown = rown2; k0 = k0n; k1 = k1n; k0n = k0nn; k1n = k1nn;
+    }
+}
+
 // persistent-style grid for the pipelined kernel: exactly the CTAs that are resident at once (occupancy query per instantiation),
 // every lane group walks many rows
 template <int CB, int SP_U, int MINB>
@@ -160,6 +226,18 @@ static unsigned spmm_pipe_grid(long long n) {
     }
     const long long groups_per_block = SP_NT / (SP_LANES * CB);
     const long long need = (n + groups_per_block - 1) / groups_per_block;
+    const long long cap = (long long)MAUS_SM_COUNT_B200 * per_sm;
+    return (unsigned)(need < cap ? need : cap);
+}
+
+template <int SP_U, int MINB>
+static unsigned spmm_pipe8_grid(long long n) {
+    static int per_sm = 0;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_packed8_kernel<SP_U, MINB>, SP_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    }
+    const long long rows_per_block = SP_NT / 32;
+    const long long need = (n + rows_per_block - 1) / rows_per_block;
     const long long cap = (long long)MAUS_SM_COUNT_B200 * per_sm;
     return (unsigned)(need < cap ? need : cap);
 }
@@ -210,9 +288,32 @@ cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* val
         csr_spmm_packed_kernel<2, 3, 4><<<dim3(spmm_pipe_grid<2, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, 0, Y, ldy, n, 0, C);
         return cudaGetLastError();
     }
-    const int groups = (C + 3) / 4;
-    spmm_pack_kernel<4><<<dim3(pgrid, groups), 256, 0, stream>>>(V, ldv, pack_ws, ncols, 0, C);
-    return csr_spmm_packed4(rowptr, colidx, vals, pack_ws, ncols * 4, Y, ldy, n, 0, C, groups, stream);
+    // full groups of 8 candidates through the 8-wide layout, the rest (<= 7) in groups of 4 behind them in the same buffer
+    static int pack8 = -1;               // MAUS_SPMM_PACK8=0: 4-wide groups only (A/B measurements); 2 / 3: register allocation variants
+    if (pack8 < 0) { const char* e = getenv("MAUS_SPMM_PACK8"); pack8 = e ? atoi(e) : 1; }
+    // measured (round 2, profiles/spmm_pack8_sweep.py, 8 / 16 candidates): -13 % at n = 125 000 and 250 000, -5 % / +2 % at 500 000,
+    // +5 % at 1 000 000 -- the 8-wide copy (128 B per column) must stay L2-resident next to the matrix stream, so it is used
+    // while all its groups together take at most 40 MB; above that the 4-wide groups (64 MB at n = 1M) are faster
+    const bool fits8 = (size_t)ncols * 128u * (size_t)(C / 8) <= (size_t)40 << 20;
+    const int g8 = (pack8 && fits8) ? C / 8 : 0;
+    const int rest = C - 8 * g8;
+    if (g8 > 0) {
+        spmm_pack_kernel<8><<<dim3(pgrid, g8), 256, 0, stream>>>(V, ldv, pack_ws, ncols, 0, 8 * g8);
+        if (pack8 == 2) csr_spmm_packed8_kernel<3, 3><<<dim3(spmm_pipe8_grid<3, 3>(n), g8), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, ncols * 8, Y, ldy, n, 0, 8 * g8);
+        else if (pack8 == 3) csr_spmm_packed8_kernel<3, 4><<<dim3(spmm_pipe8_grid<3, 4>(n), g8), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, ncols * 8, Y, ldy, n, 0, 8 * g8);
+        else csr_spmm_packed8_kernel<3, 2><<<dim3(spmm_pipe8_grid<3, 2>(n), g8), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, ncols * 8, Y, ldy, n, 0, 8 * g8);
+        if (cudaGetLastError() != cudaSuccess) return cudaGetLastError();
+    }
+    if (rest == 0) return cudaGetLastError();
+    cplx* ws4 = pack_ws + (size_t)ncols * 8 * g8;
+    if (rest == 1) {
+        csr_spmm_packed_kernel<1, 3, 4><<<dim3(spmm_pipe_grid<1, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V + (long long)(8 * g8) * ldv, 0,
+                                                                                            Y + (long long)(8 * g8) * ldy, ldy, n, 0, 1);
+        return cudaGetLastError();
+    }
+    const int groups = (rest + 3) / 4;
+    spmm_pack_kernel<4><<<dim3(pgrid, groups), 256, 0, stream>>>(V + (long long)(8 * g8) * ldv, ldv, ws4, ncols, 0, rest);
+    return csr_spmm_packed4(rowptr, colidx, vals, ws4, ncols * 4, Y + (long long)(8 * g8) * ldy, ldy, n, 0, rest, groups, stream);
 }
 
 // number of complex elements of the interleaved copy csr_spmm needs for C candidates

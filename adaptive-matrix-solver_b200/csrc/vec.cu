@@ -477,6 +477,23 @@ __host__ inline int vmb_blocks(int n) {
     const int want = (n + RED_NT * 8 - 1) / (RED_NT * 8);      // >= 8 elements per thread
     return want < 1 ? 1 : (want > VMB_MAXBLK ? VMB_MAXBLK : want);
 }
+// Blocks per candidate when C candidates are reduced in one launch: these kernels run for 40 - 200 us, so a partly filled last
+// wave of CTAs costs up to a third of the run time (8 candidates x 64 blocks = 512 CTAs = 3.46 per SM: the SMs that got four set
+// the time).  Among the counts between half the cap and the cap, take the one whose CTA total fills whole waves best (a
+// deterministic function of n and C, like the summation order it implies).
+__host__ inline int vmb_blocks(int n, int C) {
+    const int cap = vmb_blocks(n);
+    if (cap < 8 || C <= 0) return cap;
+    int best = cap; double best_eff = 0.0;
+    for (int nb = cap; nb >= (cap + 1) / 2; --nb) {
+        const long long ctas = (long long)nb * C;
+        const long long waves = (ctas + MAUS_SM_COUNT_B200 - 1) / MAUS_SM_COUNT_B200;
+        const double eff = (double)ctas / (double)(waves * MAUS_SM_COUNT_B200);
+        if (eff >= 0.97) return nb;                        // the largest count that is balanced to 3 %
+        if (eff > best_eff) { best_eff = eff; best = nb; }
+    }
+    return best;
+}
 
 // ---- Gram matrix of converged candidates (dedup tests |<v_i, v_j>| > 0.999, AMS:436, 450, 515, 520) ----------------------
 // G[i][j] = sum_k conj(v_i[k]) v_j[k] (= np.vdot(v_i, v_j)).  One CTA per (i, group of GR_J columns j): v_i is read once per
@@ -532,7 +549,7 @@ cudaError_t vec_rq_finish(const cplx* V, const cplx* Y, int n, int C, cplx* lamb
                           double* scratch, cudaStream_t stream, int scratch_cap) {
     if (C <= 0) return cudaSuccess;
     if (scratch && n >= VMB_MIN_N) {
-        const int nblk = vmb_blocks(n);
+        const int nblk = vmb_blocks(n, C);
         rq_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, scratch, scratch_cap > 0 ? scratch_cap : 0, lambda, vnorm2, status);
         if (scratch_cap <= 0) rq_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(scratch, nblk, C, lambda, vnorm2, status);
         return cudaGetLastError();
@@ -545,7 +562,7 @@ cudaError_t vec_mix_normalise(cplx* V, const cplx* X, int n, int C, int problem_
                               double* mixnorm, int* status, double* scratch, cudaStream_t stream) {
     if (C <= 0) return cudaSuccess;
     if (scratch && n >= VMB_MIN_N) {
-        const int nblk = vmb_blocks(n);
+        const int nblk = vmb_blocks(n, C);
         mix_preset_kernel<<<(C + 127) / 128, 128, 0, stream>>>(status, C, scratch);
         mix_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, X, n, alpha, status, scratch);
         mix_apply_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, n, problem_type, mixnorm, status, scratch);
@@ -559,7 +576,7 @@ cudaError_t vec_residual_finish(const cplx* V, const cplx* Y, int n, int C, int 
                                 const cplx* b, double* resid, double* scratch, cudaStream_t stream, int scratch_cap) {
     if (C <= 0) return cudaSuccess;
     if (scratch && n >= VMB_MIN_N) {
-        const int nblk = vmb_blocks(n);
+        const int nblk = vmb_blocks(n, C);
         res_part_kernel<<<dim3(nblk, C), RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch, scratch_cap > 0 ? scratch_cap : 0, resid);
         if (scratch_cap <= 0) res_final_kernel<<<C, RED_NT, 0, stream>>>(V, Y, n, problem_type, lambda, b, scratch, nblk, resid);
         return cudaGetLastError();

@@ -48,7 +48,7 @@ if "spmm" in sections:
     n = 1_000_000
     A = k5_sparse(n)
     eng.set_matrix(A)
-    for C_ in (1, 4):
+    for C_ in (1, 4, 8):       # 8: one pass through the 128-byte-per-entry layout (csr_spmm_packed8_kernel)
         matvec_roofline("csr_spmm_kernel", C_, 20, 20.0 * A.nnz + 8.0 * (n + 1) + 32.0 * n * C_)
 
 if "vec" in sections:

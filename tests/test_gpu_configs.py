@@ -165,3 +165,31 @@ def test_k5_sparse_population_step_through_seam_b_full_size(eng):
         assert np.linalg.norm(A @ xs - b) <= 2e-8 * nb
         r = np.linalg.norm(A @ c.x_k - b)
         assert abs(c.residual_k - r) <= 1e-10 * max(r, 1.0)
+
+
+@pytest.mark.parametrize("C", [2, 3, 8, 9, 13, 16])
+def test_spmm_candidate_groups_match_scipy(eng, C):
+    """SpMM through every grouping of the candidate block (groups of 8 through the 128-byte-per-entry layout, groups of 4 / 2,
+    a single candidate behind them) on a ragged matrix: empty rows, one-entry rows, rows longer than one 24-entry chunk.  The
+    Rayleigh quotient and the residual norm see every entry of A V; n is above the multi-block threshold of the reductions."""
+    from adaptive_matrix_solver_b200 import _abi
+    n = 40_000
+    rng = np.random.default_rng(11 + C)
+    counts = rng.choice([0, 1, 5, 21, 24, 25, 49, 60], size=n, p=[0.05, 0.05, 0.2, 0.4, 0.1, 0.1, 0.05, 0.05])
+    rows = np.repeat(np.arange(n), counts)
+    cols = rng.integers(0, n, size=rows.size)
+    vals = (rng.random(rows.size) - 0.5) + 1j * (rng.random(rows.size) - 0.5)
+    A = sp.csc_matrix(sp.coo_matrix((vals, (rows, cols)), shape=(n, n)))
+    V = rng.random((C, n)) + 1j * rng.random((C, n)); V /= np.linalg.norm(V, axis=1, keepdims=True)
+    eng.set_matrix(A)
+    eng.upload_vectors(V)
+    lam, vn2 = eng.rq(C_=C)
+    AV = (A @ V.T).T
+    for c in range(C):
+        ref = np.vdot(V[c], AV[c])
+        assert abs(lam[c] - ref) <= 1e-12 * max(abs(ref), 1.0), (c, lam[c], ref)
+        assert abs(vn2[c] - 1) <= 1e-12
+    r = eng.residual(_abi.EIGENVALUE, lam=lam, C_=C)
+    for c in range(C):
+        ref = np.linalg.norm(AV[c] - lam[c] * V[c])
+        assert abs(r[c] - ref) <= 1e-11 * ref, (c, r[c], ref)
