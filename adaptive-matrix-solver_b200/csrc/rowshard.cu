@@ -796,7 +796,7 @@ extern "C" int maus_rs_step(maus_ctx* ctx, int64_t C, int problem_type, int phas
     if (do_res) {
         if ((rc = rs_matvec(ctx, rs, rs->V, nl, rs->Y, nl, C))) return rc;
         MAUS_CUDA(ctx, vec_res_part(rs->V, rs->Y, (int)nl, (int)C, problem_type, rs->lambda, rs->b, rs->scratch, nblk, st));
-        if ((rc = rs_reduce_records(ctx, rs, rs->scratch, cs, 4, nblk, 4, 0x9u, 0x4u, 0, C))) return rc;
+        if ((rc = rs_reduce_records(ctx, rs, rs->scratch, cs, 4, nblk, 2, 0x0u, 0x1u, 0, C))) return rc;      // component 1: sum of squares
         MAUS_CUDA(ctx, vec_res_final(rs->V, rs->Y, (int)nl, (int)C, problem_type, rs->lambda, rs->b, rs->scratch, nblk, rs->resid, st));
         ctx->launches += 2;
     }

@@ -248,14 +248,10 @@ __device__ __forceinline__ double vmb_sum(const double* part, int nblk, int k) {
     for (int q = 0; q < nblk; ++q) s += __ldcg(&part[q * 4 + k]);      // L2: written by other blocks (of this launch, when fused)
     return s;
 }
-__device__ __forceinline__ double vmb_max(const double* part, int nblk, int k) {
-    double s = 0.0;
-    for (int q = 0; q < nblk; ++q) s = fmax(s, __ldcg(&part[q * 4 + k]));
-    return s;
-}
 
-// The 2-norms are accumulated UNSCALED in the same pass that finds max |component|; the scaled (dznrm2-like, overflow-safe)
-// sum of the one-CTA kernels is only recomputed when the plain sum left the safe range (never for normalised vectors).
+// The 2-norms are accumulated UNSCALED (six FMAs per element, nothing else on the FP64 pipe); the scaled (dznrm2-like,
+// overflow-safe) sum of the one-CTA kernels -- with its maximum and NaN scan -- is only recomputed when the plain sum left the
+// safe range (never for normalised vectors).
 __device__ __forceinline__ bool vmb_ss_safe(double ss) { return isfinite(ss) && ss > 1e-290; }
 
 // block-done counters live behind the partials: scratch[C * VMB_MAXBLK * 4 + c] (zero-initialised, reset by the last block)
@@ -334,7 +330,7 @@ __global__ void __launch_bounds__(RED_NT) mix_part_kernel(cplx* __restrict__ V, 
     cplx* v = V + (long long)c * n;
     const cplx* x = X + (long long)c * n;
     const double a = alpha[c], oma = 1.0 - a;
-    double amax = 0.0, ss = 0.0;
+    double ss = 0.0;
     for (int i = i0 + threadIdx.x; i < i1; i += 4 * RED_NT) {
         cplx vi[4], xi[4];
 #pragma unroll
@@ -348,18 +344,28 @@ __global__ void __launch_bounds__(RED_NT) mix_part_kernel(cplx* __restrict__ V, 
             const int k = i + u * RED_NT;
             const cplx m = cmake(oma * vi[u].x + a * xi[u].x, oma * vi[u].y + a * xi[u].y);
             if (k < i1) v[k] = m;
-            amax = fmax(amax, fmax(fabs(m.x), fabs(m.y)));
             ss = fma(m.x, m.x, ss); ss = fma(m.y, m.y, ss);
         }
     }
-    amax = block_max(amax, sh); ss = block_sum(ss, sh);
+    ss = block_sum(ss, sh);
     if (threadIdx.x == 0) {
         double* o = scratch + ((long long)c * VMB_MAXBLK + blockIdx.x) * 4;
-        o[0] = amax; o[1] = ss;
+        o[0] = 0.0; o[1] = ss;       // o[0] >= 0: "not skipped" (mix_preset); the maximum is found by the rare slow path itself
     }
 }
 // scaled 2-norm of a whole vector by ONE block (rare fallback when the plain sum of squares over- / underflowed)
-__device__ double vmb_scaled_norm_slow(const cplx* __restrict__ v, int n, double amax, double* sh) {
+__device__ double vmb_scaled_norm_slow(const cplx* __restrict__ v, int n, double* sh) {
+    double amax = 0.0;
+    bool nan_seen = false;
+    for (int i = threadIdx.x; i < n; i += RED_NT) {
+        const cplx m = v[i];
+        if (m.x != m.x || m.y != m.y) nan_seen = true;
+        amax = fmax(amax, fmax(fabs(m.x), fabs(m.y)));
+    }
+    amax = block_max(amax, sh);
+    const double anynan = block_max(nan_seen ? 1.0 : 0.0, sh);
+    if (anynan > 0.0) return nan("");
+    if (!(amax > 0.0) || !isfinite(amax)) return amax;
     const double inv = 1.0 / amax;
     double ss = 0.0;
     for (int i = threadIdx.x; i < n; i += RED_NT) {
@@ -380,12 +386,10 @@ __global__ void __launch_bounds__(RED_NT) mix_apply_kernel(cplx* __restrict__ V,
     if (part[0] < 0.0) { if (blockIdx.x == 0 && threadIdx.x == 0 && mixnorm) mixnorm[c] = 0.0; return; }
     int i0, i1; vmb_range(n, gridDim.x, blockIdx.x, i0, i1);
     cplx* v = V + (long long)c * n;
-    const double amax = vmb_max(part, gridDim.x, 0);
+    // plain sum of squares; outside its safe range (zero vector, over- / underflow, inf / nan) every block recomputes the same
+    // scaled (dznrm2-like) value from the whole vector
     const double ss = vmb_sum(part, gridDim.x, 1);
-    double nv;
-    if (!(amax > 0.0) || !isfinite(amax)) nv = amax;
-    else if (vmb_ss_safe(ss)) nv = sqrt(ss);
-    else nv = vmb_scaled_norm_slow(v, n, amax, sh);          // every block recomputes the same value
+    const double nv = vmb_ss_safe(ss) ? sqrt(ss) : ((ss != ss) ? ss : vmb_scaled_norm_slow(v, n, sh));
     if (blockIdx.x == 0 && threadIdx.x == 0 && mixnorm) mixnorm[c] = nv;
     if (problem_type == MAUS_EIGENVALUE) {
         if (nv > 1e-10) {                                    // AMS:282
@@ -404,27 +408,42 @@ __global__ void mix_preset_kernel(const int* __restrict__ status, int C, double*
 // final value of candidate c from the partials of nblk blocks; executed by a whole block (the rare scaled recomputation walks the vector)
 __device__ void res_final_body(const cplx* __restrict__ V, const cplx* __restrict__ Y, int n, int problem_type, const cplx* __restrict__ lambda,
                                const cplx* __restrict__ b, const double* part, int nblk, int c, double* resid, double* sh) {
-    const double amax = vmb_max(part, nblk, 0), ss = vmb_sum(part, nblk, 1), bad = vmb_max(part, nblk, 3);
+    const double ss = vmb_sum(part, nblk, 1);
     double out;
-    if (bad > 0.0) out = nan("");                            // np.linalg.norm propagates NaN (fmax would drop it)
-    else if (!(amax > 0.0) || !isfinite(amax)) out = amax;
-    else if (vmb_ss_safe(ss)) out = sqrt(ss);
+    if (vmb_ss_safe(ss)) out = sqrt(ss);
+    else if (ss != ss) out = ss;          // NaN in y or v (np.linalg.norm propagates it); decided on the combined sum, so that
+                                          // the ranks of a row-sharded vector agree
     else {
-        // rare: recompute with the scaled sum (this block alone walks the vector)
+        // rare (zero residual, over- / underflow, inf / nan): this block alone walks the vector: NaN test and maximum, then the
+        // scaled sum.  np.linalg.norm propagates NaN (fmax would drop it).
         const cplx* v = V + (long long)c * n;
         const cplx* y = Y + (long long)c * n;
         const bool eig = problem_type == MAUS_EIGENVALUE;
         const cplx lam = eig ? lambda[c] : cmake(0.0, 0.0);
-        const double inv = 1.0 / amax;
-        double s2 = 0.0;
+        double amax = 0.0, bad = 0.0;
         for (int i = threadIdx.x; i < n; i += RED_NT) {
             cplx r = y[i];
-            if (eig) cfms(r, lam, v[i]); else r = csub(r, b[i]);
-            const double p = r.x * inv, q = r.y * inv;
-            s2 = fma(p, p, s2); s2 = fma(q, q, s2);
+            const cplx w = v[i];
+            if (r.x != r.x || r.y != r.y || w.x != w.x || w.y != w.y) bad = 1.0;
+            if (eig) cfms(r, lam, w); else r = csub(r, b[i]);
+            if (r.x != r.x || r.y != r.y) bad = 1.0;
+            amax = fmax(amax, fmax(fabs(r.x), fabs(r.y)));
         }
-        s2 = block_sum(s2, sh);
-        out = amax * sqrt(s2);
+        amax = block_max(amax, sh); bad = block_max(bad, sh);
+        if (bad > 0.0) out = nan("");
+        else if (!(amax > 0.0) || !isfinite(amax)) out = amax;
+        else {
+            const double inv = 1.0 / amax;
+            double s2 = 0.0;
+            for (int i = threadIdx.x; i < n; i += RED_NT) {
+                cplx r = y[i];
+                if (eig) cfms(r, lam, v[i]); else r = csub(r, b[i]);
+                const double p = r.x * inv, q = r.y * inv;
+                s2 = fma(p, p, s2); s2 = fma(q, q, s2);
+            }
+            s2 = block_sum(s2, sh);
+            out = amax * sqrt(s2);
+        }
     }
     if (threadIdx.x == 0) resid[c] = out;
 }
@@ -439,28 +458,27 @@ __global__ void __launch_bounds__(RED_NT) res_part_kernel(const cplx* __restrict
     const cplx* y = Y + (long long)c * n;
     const bool eig = problem_type == MAUS_EIGENVALUE;
     const cplx lam = eig ? lambda[c] : cmake(0.0, 0.0);
-    double amax = 0.0, ss = 0.0, bad = 0.0;
+    // one pass, six FMAs per element: r = y - lambda v (eigen) / y - b (linear) and the plain sum of squares.  A NaN in y or v
+    // reaches the sum through r, an overflow makes it inf, a zero residual leaves 0: all three send the final step to its slow path
+    double ss = 0.0;
     for (int i = i0 + threadIdx.x; i < i1; i += 4 * RED_NT) {
-        cplx r[4], w[4], bb[4];
+        cplx r[4], w[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = i + u * RED_NT;
             r[u] = (k < i1) ? __ldcs(&y[k]) : cmake(0.0, 0.0);
-            w[u] = (k < i1) ? v[k] : cmake(0.0, 0.0);
-            bb[u] = (!eig && k < i1) ? b[k] : cmake(0.0, 0.0);
+            w[u] = (k < i1) ? (eig ? v[k] : b[k]) : cmake(0.0, 0.0);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (r[u].x != r[u].x || r[u].y != r[u].y || w[u].x != w[u].x || w[u].y != w[u].y) bad = 1.0;
-            if (eig) cfms(r[u], lam, w[u]); else r[u] = csub(r[u], bb[u]);
-            amax = fmax(amax, fmax(fabs(r[u].x), fabs(r[u].y)));
+            if (eig) cfms(r[u], lam, w[u]); else r[u] = csub(r[u], w[u]);
             ss = fma(r[u].x, r[u].x, ss); ss = fma(r[u].y, r[u].y, ss);
         }
     }
-    amax = block_max(amax, sh); ss = block_sum(ss, sh); bad = block_max(bad, sh);
+    ss = block_sum(ss, sh);
     if (threadIdx.x == 0) {
         double* o = scratch + ((long long)c * VMB_MAXBLK + blockIdx.x) * 4;
-        o[0] = amax; o[1] = ss; o[3] = bad;
+        o[1] = ss;
     }
     if (fuse_C > 0 && vmb_last_block(scratch, fuse_C, c))
         res_final_body(V, Y, n, problem_type, lambda, b, scratch + (long long)c * VMB_MAXBLK * 4, gridDim.x, c, resid, sh);
