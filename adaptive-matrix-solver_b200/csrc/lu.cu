@@ -652,6 +652,90 @@ __global__ void __launch_bounds__(BS_NT) lu_backsolve_kernel(const cplx* __restr
     }
 }
 
+// Back substitution for SMALL batches: one CTA per candidate streams the whole upper triangle (n^2 / 2 entries) through a single
+// SM, ~38 GB/s, 3.3 - 3.6 ms at n = 4096 however few candidates there are.  Here a CLUSTER of NC CTAs shares one candidate:
+// the 32-row blocks are owned block-cyclically (block kb -> CTA kb % NC), every CTA keeps the y entries of its own blocks in
+// shared memory, the owner of block kb solves its 32 x 32 triangle and writes x_kb into every CTA's shared memory (DSMEM), one
+// cluster barrier per block step, then every CTA subtracts U[own rows, block kb] x_kb from its y.  Same arithmetic per row as
+// lu_backsolve_kernel except that the diagonal is applied as a reciprocal (one division per diagonal entry, computed by 32
+// lanes at once instead of a Smith division inside the 32-step dependent chain).
+__global__ void __launch_bounds__(BS_NT) lu_backsolve_cluster_kernel(const cplx* __restrict__ W, long long strideW, int n,
+                                                                     const int* __restrict__ info, cplx* __restrict__ X,
+                                                                     int* __restrict__ status) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int NC = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    extern __shared__ __align__(16) unsigned char bs_smem[];
+    cplx* yloc = reinterpret_cast<cplx*>(bs_smem);        // [owned blocks][32]
+    __shared__ cplx xb[2][BS_BLK];
+    __shared__ cplx D[BS_BLK][BS_BLK + 1];
+    __shared__ int bad[PANEL_MAXC];                        // rank 0 collects one flag per CTA
+    const int b = blockIdx.x / NC, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const cplx* Wb = W + (long long)b * strideW;
+    const int nblk = (n + BS_BLK - 1) / BS_BLK;
+    const int nown = (nblk - rank + NC - 1) / NC;          // blocks rank, rank + NC, ...
+    for (int idx = tid; idx < nown * BS_BLK; idx += BS_NT) {
+        const int i = ((idx / BS_BLK) * NC + rank) * BS_BLK + (idx % BS_BLK);
+        yloc[idx] = (i < n) ? Wb[i + (long long)n * n] : cmake(0.0, 0.0);
+    }
+    int mybad = 0;
+    __syncthreads();
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int r0 = kb * BS_BLK, bs = min(BS_BLK, n - r0), buf = kb & 1;
+        if (kb % NC == rank) {
+            for (int idx = tid; idx < bs * bs; idx += BS_NT) {
+                const int i = idx % bs, j = idx / bs;
+                D[i][j] = Wb[(r0 + i) + (long long)(r0 + j) * n];
+            }
+            __syncthreads();
+            if (warp == 0) {
+                cplx yi = (lane < bs) ? yloc[(kb / NC) * BS_BLK + lane] : cmake(0.0, 0.0);
+                const cplx rinv = (lane < bs) ? pivot_recip(D[lane][lane]) : cmake(0.0, 0.0);
+                for (int j = bs - 1; j >= 0; --j) {
+                    const cplx yj = cmake(__shfl_sync(0xffffffffu, yi.x, j), __shfl_sync(0xffffffffu, yi.y, j));
+                    const cplx rj = cmake(__shfl_sync(0xffffffffu, rinv.x, j), __shfl_sync(0xffffffffu, rinv.y, j));
+                    const cplx xj = cmul(yj, rj);
+                    if (lane == j) yi = xj;
+                    else if (lane < j) cfms(yi, D[lane][j], xj);
+                }
+                if (lane < bs) {
+                    if (!cfinite(yi)) mybad = 1;
+                    X[(long long)b * n + r0 + lane] = yi;
+                    for (int d = 0; d < NC; ++d) *cluster.map_shared_rank(&xb[buf][lane], d) = yi;
+                }
+            }
+        }
+        cluster.sync();          // x_kb has landed everywhere; everybody has finished reading the buffer it replaces (step kb + 2)
+        // own row blocks above block kb: 16 of them per pass, one warp each, one row per lane
+        for (int ob = warp; ob * NC + rank < kb; ob += BS_NT / 32) {
+            const int i = (ob * NC + rank) * BS_BLK + lane;             // < r0 <= n - 1
+            cplx acc = yloc[ob * BS_BLK + lane];
+            const cplx* u = Wb + i + (long long)r0 * n;
+            if (bs == BS_BLK) {
+                cplx uu[BS_BLK];
+#pragma unroll
+                for (int j = 0; j < BS_BLK; ++j) uu[j] = __ldcs(&u[(long long)j * n]);
+#pragma unroll
+                for (int j = 0; j < BS_BLK; ++j) cfms(acc, uu[j], xb[buf][j]);
+            } else {
+                for (int j = 0; j < bs; ++j) cfms(acc, __ldg(&u[(long long)j * n]), xb[buf][j]);
+            }
+            yloc[ob * BS_BLK + lane] = acc;
+        }
+        __syncthreads();         // the owner of block kb - 1 reads its y entries next; D is rewritten
+    }
+    if (mybad) *cluster.map_shared_rank(&bad[rank], 0) = 1;
+    else if (tid == 0) *cluster.map_shared_rank(&bad[rank], 0) = 0;
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+        int any = 0;
+        for (int d = 0; d < NC; ++d) any |= bad[d];
+        if (status[b] == 0) {
+            if (info[b] != 0) status[b] = MAUS_ST_ZERO_PIVOT;
+            else if (any) status[b] = MAUS_ST_NONFINITE;
+        }
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
@@ -749,6 +833,31 @@ cudaError_t lu_trtri(const cplx* W, long long strideW, int n, int k0, int jb, in
 
 cudaError_t lu_backsolve(const cplx* W, long long strideW, int n, int batch, const int* info, cplx* X, int* status,
                          cudaStream_t stream) {
+    // small batches: a cluster of CTAs per candidate (the largest power of two that still gives every CTA its own SM)
+    static int use_cluster = -1;            // MAUS_BACKSOLVE_CLUSTER=0: one CTA per candidate always (A/B measurements)
+    if (use_cluster < 0) { const char* e = getenv("MAUS_BACKSOLVE_CLUSTER"); use_cluster = e ? (atoi(e) != 0) : 1; }
+    int nc = 1;
+    while (use_cluster && nc < PANEL_MAXC && batch * nc * 2 <= MAUS_SM_COUNT_B200) nc *= 2;
+    if (nc > 1 && n >= 8 * BS_BLK) {
+        const int nblk = (n + BS_BLK - 1) / BS_BLK;
+        const size_t smem = (size_t)((nblk + nc - 1) / nc) * BS_BLK * sizeof(cplx);
+        static size_t attr_smem_c = 0;
+        if (smem > attr_smem_c) {
+            cudaError_t e = cudaFuncSetAttribute(lu_backsolve_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_smem_c = smem;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(batch * nc, 1, 1);
+        cfg.blockDim = dim3(BS_NT, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, lu_backsolve_cluster_kernel, W, strideW, n, info, X, status);
+    }
     const size_t smem = ((size_t)n + BS_BLK * (BS_BLK + 1)) * sizeof(cplx);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static size_t attr_smem = 0;
