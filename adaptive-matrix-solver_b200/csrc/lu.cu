@@ -17,6 +17,7 @@
 //   lu_trtri        inverse of the unit-lower 128 x 128 diagonal block, so that the triangular solve for U12 and the
 //                   trailing update are both plain GEMMs on the FP64 tensor pipe (zgemm.cu).
 #include <cooperative_groups.h>
+#include <algorithm>
 #include <cstdlib>
 #include "lu.cuh"
 #include "../../include/maus_b200.h"
@@ -529,52 +530,52 @@ __global__ void __launch_bounds__(LU_NB * TRTRI_SPLIT) lu_trtri_kernel(const cpl
         __syncthreads();       // X row complete; ring slot rl % PF may be refilled by the next fetch
     }
     // ---- phase B: off-diagonal blocks, level by level: X21 = -X22 * (L21 * X11) for the pair of hh x hh blocks at offset o ----
-    // executed by the nt threads [t0, t0 + nt) (warp-aligned); both __syncthreads are reached by every thread of the CTA
-    auto pair_product = [&](int o, int hh, int t0, int nt) {
+    // executed by the nt threads [t0, t0 + nt) (warp-aligned); both __syncthreads are reached by every thread of the CTA.
+    // T = L21 X11 goes into its own buffer Tb (hh x (hh + 1), aliases the row ring of phase A), so the second product is a plain
+    // triangular matrix product spread over all threads (round 2: it ran in place, row by row from the bottom up -- hh sequential
+    // steps of an 8-lane dot product, 35 k of the kernel's 165 k cycles at jb = 128)
+    auto pair_product = [&](int o, int hh, int t0, int nt, cplx* Tb) {
         const int tl = (int)threadIdx.x - t0;
         const bool mine = tl >= 0 && tl < nt;
-        // T[i][j] = sum_{p = j}^{hh-1} L21[i][p] X11[p][j]  -> slot of X21[i][j]; thread tl: row i = tl % hh, columns j = tl / hh + u * (nt / hh)
+        const int ldt = hh + 1;
+        // T[i][j] = sum_{p = j}^{hh-1} L21[i][p] X11[p][j]; thread tl: row i = tl % hh, columns j = tl / hh + u * (nt / hh)
         if (mine) {
             const int i = tl % hh;
             const cplx* l21 = L + (o + hh + i) + (long long)o * n;     // L21[i][p] = l21[p * n] (consecutive threads, consecutive rows)
             for (int j = tl / hh; j < hh; j += nt / hh) {
                 cplx acc = cmake(0.0, 0.0);
+#pragma unroll 4
                 for (int p = j; p < hh; ++p) cfma(acc, __ldg(&l21[(long long)p * n]), X[((o + p) * (o + p + 1)) / 2 + o + j]);
-                X[((o + hh + i) * (o + hh + i + 1)) / 2 + o + j] = acc;
+                Tb[i * ldt + j] = acc;
             }
         }
         __syncthreads();
-        // X21[i][j] = -sum_{q <= i} X22[i][q] T[q][j], rows from the bottom up so that T[q <= i][j] is still intact; column j
-        // is owned by a group of 8 lanes (dot product split over them)
-        {
-            const int j = tl >> 3, l8 = tl & 7;
-            const bool col = mine && j < hh;
-            for (int i = hh - 1; i >= 0; --i) {
-                cplx acc = cmake(0.0, 0.0);
+        // X21[i][j] = -sum_{q <= i} X22[i][q] T[q][j]; thread tl: column j = tl % hh (T and X21 contiguous over the warp, X22[i][q] a
+        // broadcast), rows i = tl / hh + u * (nt / hh); two accumulators halve the dependent FMA chain
+        if (mine) {
+            const int j = tl % hh;
+            for (int i = tl / hh; i < hh; i += nt / hh) {
                 const int ri = o + hh + i;
-                if (col) {
-                    const cplx* x22 = X + (ri * (ri + 1)) / 2 + o + hh;          // X22[i][q], q <= i
-                    for (int q = l8; q <= i; q += 8) cfma(acc, x22[q], X[((o + hh + q) * (o + hh + q + 1)) / 2 + o + j]);
-                }
-#pragma unroll
-                for (int s8 = 4; s8 > 0; s8 >>= 1) {
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s8); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s8);
-                }
-                if (col && l8 == 0) X[(ri * (ri + 1)) / 2 + o + j] = cmake(-acc.x, -acc.y);
-                __syncwarp();
+                const cplx* x22 = X + (ri * (ri + 1)) / 2 + o + hh;              // X22[i][q], q <= i
+                cplx a0 = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0);
+                int q = 0;
+                for (; q + 1 <= i; q += 2) { cfma(a0, x22[q], Tb[q * ldt + j]); cfma(a1, x22[q + 1], Tb[(q + 1) * ldt + j]); }
+                if (q <= i) cfma(a0, x22[q], Tb[q * ldt + j]);
+                X[(ri * (ri + 1)) / 2 + o + j] = cmake(-(a0.x + a1.x), -(a0.y + a1.y));
             }
         }
         __syncthreads();
     };
     {
         const int NT = LU_NB * TRTRI_SPLIT;
+        cplx* Tb = rowbuf;                                               // phase A is over: the row ring is free
         if (nblk == 4) {
             // level 1: the two pairs of h-blocks side by side (half of the CTA each), level 2: the pair of 2h-blocks
             const int upper = ((int)threadIdx.x < NT / 2) ? 0 : 1;        // one call site: every thread passes the same barriers
-            pair_product(upper * 2 * h, h, upper * (NT / 2), NT / 2);
-            pair_product(0, 2 * h, 0, NT);
+            pair_product(upper * 2 * h, h, upper * (NT / 2), NT / 2, Tb + upper * (h * (h + 1)));
+            pair_product(0, 2 * h, 0, NT, Tb);
         } else if (nblk == 2) {
-            pair_product(0, h, 0, NT);
+            pair_product(0, h, 0, NT, Tb);
         }
     }
     cplx* out = Linv + (long long)b * LU_NB * LU_NB;
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(BS_NT) lu_backsolve_cluster_kernel(const cplx*
     extern __shared__ __align__(16) unsigned char bs_smem[];
     cplx* yloc = reinterpret_cast<cplx*>(bs_smem);        // [owned blocks][32]
     __shared__ cplx xb[2][BS_BLK];
-    __shared__ cplx D[BS_BLK][BS_BLK + 1];
+    __shared__ cplx D[2][BS_BLK][BS_BLK + 1];              // diagonal blocks: the one being solved and the owner's next one
     __shared__ int bad[PANEL_MAXC];                        // rank 0 collects one flag per CTA
     const int b = blockIdx.x / NC, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const cplx* Wb = W + (long long)b * strideW;
@@ -677,32 +678,41 @@ __global__ void __launch_bounds__(BS_NT) lu_backsolve_cluster_kernel(const cplx*
         const int i = ((idx / BS_BLK) * NC + rank) * BS_BLK + (idx % BS_BLK);
         yloc[idx] = (i < n) ? Wb[i + (long long)n * n] : cmake(0.0, 0.0);
     }
+    // the diagonal blocks are final before this kernel starts: the owner fetches its next one while it solves the current one
+    auto fetch_D = [&](int kq, int slot, int t0, int nt) {
+        if (kq < 0) return;
+        const int q0 = kq * BS_BLK, qs = min(BS_BLK, n - q0);
+        for (int idx = tid - t0; idx >= 0 && idx < qs * qs; idx += nt) {
+            const int i = idx % qs, j = idx / qs;
+            D[slot][i][j] = Wb[(q0 + i) + (long long)(q0 + j) * n];
+        }
+    };
+    int dcur = 0;
+    if (nown > 0) fetch_D((nown - 1) * NC + rank, 0, 0, BS_NT);
     int mybad = 0;
     __syncthreads();
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const int r0 = kb * BS_BLK, bs = min(BS_BLK, n - r0), buf = kb & 1;
         if (kb % NC == rank) {
-            for (int idx = tid; idx < bs * bs; idx += BS_NT) {
-                const int i = idx % bs, j = idx / bs;
-                D[i][j] = Wb[(r0 + i) + (long long)(r0 + j) * n];
-            }
-            __syncthreads();
             if (warp == 0) {
                 cplx yi = (lane < bs) ? yloc[(kb / NC) * BS_BLK + lane] : cmake(0.0, 0.0);
-                const cplx rinv = (lane < bs) ? pivot_recip(D[lane][lane]) : cmake(0.0, 0.0);
+                const cplx rinv = (lane < bs) ? pivot_recip(D[dcur][lane][lane]) : cmake(0.0, 0.0);
                 for (int j = bs - 1; j >= 0; --j) {
                     const cplx yj = cmake(__shfl_sync(0xffffffffu, yi.x, j), __shfl_sync(0xffffffffu, yi.y, j));
                     const cplx rj = cmake(__shfl_sync(0xffffffffu, rinv.x, j), __shfl_sync(0xffffffffu, rinv.y, j));
                     const cplx xj = cmul(yj, rj);
                     if (lane == j) yi = xj;
-                    else if (lane < j) cfms(yi, D[lane][j], xj);
+                    else if (lane < j) cfms(yi, D[dcur][lane][j], xj);
                 }
                 if (lane < bs) {
                     if (!cfinite(yi)) mybad = 1;
                     X[(long long)b * n + r0 + lane] = yi;
                     for (int d = 0; d < NC; ++d) *cluster.map_shared_rank(&xb[buf][lane], d) = yi;
                 }
+            } else {
+                fetch_D(kb - NC, dcur ^ 1, 32, BS_NT - 32);
             }
+            dcur ^= 1;
         }
         cluster.sync();          // x_kb has landed everywhere; everybody has finished reading the buffer it replaces (step kb + 2)
         // own row blocks above block kb: 16 of them per pass, one warp each, one row per lane
@@ -820,7 +830,8 @@ cudaError_t lu_permute_rows(cplx* W, long long strideW, int n, int k0, int colst
 }
 
 cudaError_t lu_trtri(const cplx* W, long long strideW, int n, int k0, int jb, int batch, cplx* Linv, cudaStream_t stream) {
-    const size_t smem = ((size_t)(LU_NB * (LU_NB + 1)) / 2 + TRTRI_PF * LU_NB) * sizeof(cplx);
+    // packed X + the larger of the phase-A row ring and the phase-B T buffer (64 x 65 at jb = 128)
+    const size_t smem = ((size_t)(LU_NB * (LU_NB + 1)) / 2 + (size_t)std::max(TRTRI_PF * LU_NB, (LU_NB / 2) * (LU_NB / 2 + 1))) * sizeof(cplx);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(lu_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
