@@ -844,11 +844,14 @@ cudaError_t lu_trtri(const cplx* W, long long strideW, int n, int k0, int jb, in
 
 cudaError_t lu_backsolve(const cplx* W, long long strideW, int n, int batch, const int* info, cplx* X, int* status,
                          cudaStream_t stream) {
-    // small batches: a cluster of CTAs per candidate (the largest power of two that still gives every CTA its own SM)
+    // a cluster of CTAs per candidate: the largest power of two that keeps the grid within two CTAs per SM
     static int use_cluster = -1;            // MAUS_BACKSOLVE_CLUSTER=0: one CTA per candidate always (A/B measurements)
     if (use_cluster < 0) { const char* e = getenv("MAUS_BACKSOLVE_CLUSTER"); use_cluster = e ? (atoi(e) != 0) : 1; }
     int nc = 1;
-    while (use_cluster && nc < PANEL_MAXC && batch * nc * 2 <= MAUS_SM_COUNT_B200) nc *= 2;
+    while (use_cluster && nc < PANEL_MAXC && batch * nc * 2 <= 2 * MAUS_SM_COUNT_B200) nc *= 2;     // up to two CTAs per SM (measured: 128 candidates x 2: 4.17 -> 2.92 ms, x 4: 3.5)
+    static int force_nc = -1;               // MAUS_BACKSOLVE_NC=k: k CTAs per candidate whatever the batch (A/B measurements)
+    if (force_nc < 0) { const char* e = getenv("MAUS_BACKSOLVE_NC"); force_nc = e ? atoi(e) : 0; }
+    if (force_nc >= 1 && force_nc <= PANEL_MAXC) nc = force_nc;
     if (nc > 1 && n >= 8 * BS_BLK) {
         const int nblk = (n + BS_BLK - 1) / BS_BLK;
         const size_t smem = (size_t)((nblk + nc - 1) / nc) * BS_BLK * sizeof(cplx);
