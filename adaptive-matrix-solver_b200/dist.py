@@ -35,9 +35,10 @@ class Shard:
         import torch.distributed as dist
         return dist
 
-    def all_gather_rows(self, local, max_rows):
+    def all_gather_rows(self, local, max_rows, reuse=False):
         """all-gather a ragged [rows_r][cols] float64 block; returns list of per-rank arrays (padded rows dropped by
-        the caller, who knows each rank's count from ``owned``)."""
+        the caller, who knows each rank's count from ``owned``).  ``reuse``: the result may live in a recycled page-locked
+        buffer that stays valid until the call after the next one (``RowShardedOperator.gather``)."""
         import torch
         if self.world == 1:
             return [local]
@@ -46,7 +47,7 @@ class Shard:
         buf[:local.shape[0]] = local
         rs = getattr(self.engine, "rowshard", None) if self.engine is not None else None
         if rs is not None and rs.world == self.world:
-            out = rs.gather(buf).reshape(self.world, max_rows, cols)
+            out = rs.gather(buf, pinned=reuse).reshape(self.world, max_rows, cols)
             return [out[r] for r in range(self.world)]
         dist = self._dist()
         t = torch.from_numpy(buf)
@@ -140,6 +141,19 @@ def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, e
         return step_population(candidates, M, b, strat_params, problem_knowledge, engine)
     n = live[0].N_diag
     eigen = live[0].problem_type.value == _abi.EIGENVALUE
+    # candidates whose vector is a view into a recycled gather buffer and that have left the live set through host logic
+    # (pruned / retired by the reference's _manage_candidates) keep their vector for good: give them their own copy now
+    views = getattr(shard, "_views", None)
+    if views is None:
+        views = shard._views = {}
+    if views:
+        live_ids = {id(c) for c in live}
+        for key in [k for k in views if k not in live_ids]:
+            c = views.pop(key)
+            if eigen and c.v_k is not None:
+                c.v_k = np.array(c.v_k, copy=True)
+            elif not eigen and c.x_k is not None:
+                c.x_k = np.array(c.x_k, copy=True)
     counts = [len(range(r, len(live), shard.world)) for r in range(shard.world)]
     mine = [live[i] for i in shard.owned(len(live))]
     hist_before = [len(c.residual_history) for c in mine]
@@ -153,16 +167,26 @@ def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, e
         local[k, :NREC] = _record(c, hist_before[k], rng_drawn)
         vec = c.v_k if eigen else c.x_k
         local[k, NREC:] = np.ascontiguousarray(vec, dtype=np.complex128).view(np.float64)
-    gathered = shard.all_gather_rows(local, max(counts))
+    gathered = shard.all_gather_rows(local, max(counts), reuse=True)
+    done = (State.CONVERGED.value, State.RETIRED.value)
     for r in range(shard.world):
         if r == shard.rank:
             continue
         for k, i in enumerate(range(r, len(live), shard.world)):
             row = gathered[r][k]
-            # a VIEW into the freshly gathered block (a new array every generation, 16-byte aligned at column NREC): no
-            # per-candidate copy of the 16 n bytes; the candidate replaces the vector object on its next step
+            # a VIEW into the gathered block (16-byte aligned at column NREC): no per-candidate copy of the 16 n bytes.  The
+            # block is one of two recycled page-locked buffers: a live candidate replaces its vector in the next generation,
+            # i.e. before this buffer's turn comes again; a candidate that just left the live set keeps its vector for good
+            # and gets its own copy.
             vec = row[NREC:].view(np.complex128)
+            if int(row[10]) in done:
+                vec = vec.copy()
+                views.pop(id(live[i]), None)
+            else:
+                views[id(live[i])] = live[i]
             _apply_record(live[i], row[:NREC], vec, eigen, State)
+    for c in mine:
+        views.pop(id(c), None)               # stepped here: the vector is this rank's own array again
     _resync_host_rng(gathered, counts)
     return len(live)
 
