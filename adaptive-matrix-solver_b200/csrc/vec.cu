@@ -650,21 +650,45 @@ static void gemv_launch(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y,
     }
 }
 
-cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
-                              cudaStream_t stream) {
-    // grid sized so that several waves of CTAs cover the 148 SMs: 8 rows per CTA below n = 8192, 16 above
-    // (four rows per warp were measured in round 2: 0.32 / 0.47 of the HBM peak at n = 4096 against 0.61 -- register pressure
-    // costs more occupancy than the halved shared-memory traffic returns)
-    if (n >= 8192) gemv_launch<2, 256>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
-    else if (C >= 2 && n >= 2048) gemv_launch<2, 128>(A_rm, V, ldv, Y, ldy, n, n, C, stream);   // several candidates: LDS-bound at RPW = 1
-    else gemv_launch<1, 256>(A_rm, V, ldv, Y, ldy, n, n, C, stream);
-    return cudaGetLastError();
+// Rows per CTA = RPW * warps.  At n = 4096 a fixed 8 rows per CTA gives 512 CTAs = 3.46 per SM: the SMs that got four set the
+// time (0.865 of a balanced grid).  The warp count (4 .. 8) is therefore chosen so that the CTAs fill whole waves of the 148 SMs
+// as well as possible (n = 4096, two rows per warp: 7 warps -> 293 CTAs = 1.98 per SM).
+template <int RPW>
+static void gemv_dispatch(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int nrows, int ncols, int C,
+                          cudaStream_t stream) {
+    int best_w = 8; double best_eff = -1.0;
+    for (int w = 8; w >= 4; --w) {
+        const long long ctas = (nrows + RPW * w - 1) / (RPW * w);
+        const long long per_sm = (ctas + MAUS_SM_COUNT_B200 - 1) / MAUS_SM_COUNT_B200;
+        const double eff = (double)ctas / (double)(per_sm * MAUS_SM_COUNT_B200);
+        if (eff > best_eff + 0.02) { best_eff = eff; best_w = w; }      // prefer the larger CTA unless a smaller one is clearly better
+    }
+    switch (best_w) {
+        case 4: gemv_launch<RPW, 128>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream); break;
+        case 5: gemv_launch<RPW, 160>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream); break;
+        case 6: gemv_launch<RPW, 192>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream); break;
+        case 7: gemv_launch<RPW, 224>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream); break;
+        default: gemv_launch<RPW, 256>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream); break;
+    }
 }
 
 cudaError_t vec_gemv_rect(const cplx* A_rm, int nrows, int ncols, const cplx* V, long long ldv, cplx* Y, long long ldy, int C,
                           cudaStream_t stream) {
-    if (nrows >= 8192) gemv_launch<2, 256>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
-    else if (C >= 2 && nrows >= 2048) gemv_launch<2, 128>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
+    // two rows per warp from 2048 rows with several candidates (LDS-bound at one row per warp) and from 8192 rows always
+    // (four rows per warp were measured in round 2: 0.32 / 0.47 of the HBM peak at n = 4096 against 0.61 -- register pressure
+    // costs more occupancy than the halved shared-memory traffic returns).  One candidate: wave-balanced CTA size (n = 8192:
+    // 0.91 -> 0.97 of the HBM peak); several candidates keep the small CTAs -- every CTA re-stages the vectors chunk by chunk,
+    // and few large CTAs per SM expose those bubbles (balanced sizes measured 0.61 -> 0.58 at n = 4096, 0.76 -> 0.68 at 8192)
+    if (C == 1) {
+        if (nrows >= 8192) gemv_dispatch<2>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
+        else gemv_dispatch<1>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
+    } else if (nrows >= 8192) gemv_launch<2, 256>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
+    else if (nrows >= 2048) gemv_launch<2, 128>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
     else gemv_launch<1, 256>(A_rm, V, ldv, Y, ldy, nrows, ncols, C, stream);
     return cudaGetLastError();
+}
+
+cudaError_t vec_gemv_rowmajor(const cplx* A_rm, const cplx* V, long long ldv, cplx* Y, long long ldy, int n, int C,
+                              cudaStream_t stream) {
+    return vec_gemv_rect(A_rm, n, n, V, ldv, Y, ldy, C, stream);
 }
