@@ -13,6 +13,7 @@ struct MatrixSlot {
     cplx* cm = nullptr;          // n x n column-major               -- LU / GEMM
     // CSR (converted from the uploaded CSC)
     long long nnz = 0;
+    int max_row = 0;             // longest CSR row (0 = unknown): selects the single-chunk SpMM kernels (spmv.cu)
     long long* rowptr = nullptr; // n+1
     int* colidx = nullptr;       // nnz
     cplx* vals = nullptr;        // nnz

@@ -370,6 +370,11 @@ extern "C" int maus_set_csc(maus_ctx* ctx, int slot, int64_t n, int64_t nnz, con
     MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.vals, (size_t)nnz * sizeof(cplx)));
     MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.diag, (size_t)n * sizeof(cplx)));
     s.nnz = nnz;
+    {
+        long long longest = 0;
+        for (long long i = 0; i < n; ++i) longest = std::max(longest, rowptr[(size_t)i + 1] - rowptr[(size_t)i]);
+        s.max_row = (int)std::min<long long>(longest, 0x7fffffffLL);
+    }
     MAUS_CUDA(ctx, cudaMemcpy(s.rowptr, rowptr.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice));
     if (nnz) {
         MAUS_CUDA(ctx, cudaMemcpy(s.colidx, colidx.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice));
@@ -466,7 +471,7 @@ int maus_apply_matrix(maus_ctx* ctx, int slot, const cplx* V, long long ldv, cpl
             MAUS_CUDA(ctx, maus_dev_alloc(ctx, (void**)&s.pack, need * sizeof(cplx)));
             s.pack_elems = need;
         }
-        MAUS_CUDA(ctx, csr_spmm(s.rowptr, s.colidx, s.vals, V, ldv, Y, ldy, n, n, (int)C, C > 1 ? s.pack : nullptr, ctx->stream));
+        MAUS_CUDA(ctx, csr_spmm(s.rowptr, s.colidx, s.vals, V, ldv, Y, ldy, n, n, (int)C, C > 1 ? s.pack : nullptr, s.max_row, ctx->stream));
         prof_end(ctx, h);
         ctx->launches += (C > 1) ? 2 : 1;          // interleave pass + one SpMM launch over all groups of 4
         return MAUS_OK;

@@ -72,6 +72,7 @@ struct RowShard {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
     long long n = 0, row0 = 0, nloc = 0, nnz = 0;
+    int max_row = 0;          // longest row of the local CSR block (selects the single-chunk SpMM kernels)
     long long* rowptr = nullptr; int* colidx = nullptr; cplx* vals = nullptr; cplx* diag = nullptr;
     double amax = 0.0;
     cplx* xfull = nullptr;                          // [C][n]: NCCL transport of the matvec input / full vectors for the host write-back
@@ -433,6 +434,8 @@ extern "C" int maus_set_csr_rowblock(maus_ctx* ctx, int64_t n, int64_t row0, int
     const long long nnz = rowptr[nrows] - rowptr[0];
     std::vector<long long> rp((size_t)nrows + 1);
     for (long long i = 0; i <= nrows; ++i) rp[(size_t)i] = rowptr[i] - rowptr[0];
+    long long longest = 0;
+    for (long long i = 0; i < nrows; ++i) longest = std::max<long long>(longest, (long long)(rowptr[i + 1] - rowptr[i]));
     std::vector<int> ci((size_t)nnz);
     std::vector<cplx> dg((size_t)nrows, cmake(0.0, 0.0));
     double amax = 0.0;
@@ -467,7 +470,7 @@ extern "C" int maus_set_csr_rowblock(maus_ctx* ctx, int64_t n, int64_t row0, int
         MAUS_CUDA(ctx, cudaMemcpy(rs->vals, vals + 2 * rowptr[0], (size_t)nnz * sizeof(cplx), cudaMemcpyHostToDevice));
     }
     MAUS_CUDA(ctx, cudaMemcpy(rs->diag, dg.data(), (size_t)nrows * sizeof(cplx), cudaMemcpyHostToDevice));
-    rs->n = n; rs->row0 = row0; rs->nloc = nrows; rs->nnz = nnz; rs->amax = amax;
+    rs->n = n; rs->row0 = row0; rs->nloc = nrows; rs->nnz = nnz; rs->amax = amax; rs->max_row = (int)std::min<long long>(longest, 0x7fffffffLL);
     return MAUS_OK;
 }
 
@@ -606,7 +609,7 @@ static int rs_matvec(maus_ctx* ctx, RowShard* rs, const cplx* v, long long ldv, 
                                                    rs->world, seq, rs->d_counter, rs->d_err);
         rs_wait_x_kernel<<<1, 32, 0, st>>>(rs->d_peer, buf, rs->rank, rs->world, seq, rs->d_err);
         const cplx* P = reinterpret_cast<const cplx*>(rs->seg + off);
-        MAUS_CUDA(ctx, csr_spmm_packed4(rs->rowptr, rs->colidx, rs->vals, P, rs->n * 4, z, ldz, rs->nloc, 0, (int)C, groups, st));
+        MAUS_CUDA(ctx, csr_spmm_packed4(rs->rowptr, rs->colidx, rs->vals, P, rs->n * 4, z, ldz, rs->nloc, 0, (int)C, groups, rs->max_row, st));
         rs_done_x_kernel<<<1, 32, 0, st>>>(rs->d_peer, rs->rank, rs->world, seq);
         MAUS_CUDA(ctx, cudaGetLastError());
         ctx->launches += 4;
@@ -618,7 +621,7 @@ static int rs_matvec(maus_ctx* ctx, RowShard* rs, const cplx* v, long long ldv, 
         ncclResult_t r3 = g_nccl.GroupEnd();                                   // the group is closed on every path
         MAUS_NCCL(ctx, r1); MAUS_NCCL(ctx, r2); MAUS_NCCL(ctx, r3);
         MAUS_CUDA(ctx, csr_spmm(rs->rowptr, rs->colidx, rs->vals, rs->xfull, rs->n, z, ldz, rs->nloc, rs->n, (int)C,
-                                C > 1 ? rs->pack : nullptr, st));
+                                C > 1 ? rs->pack : nullptr, rs->max_row, st));
         ctx->launches += 2;
     }
     prof_end(ctx, h);

@@ -86,7 +86,11 @@ __global__ void __launch_bounds__(256) spmm_pack_kernel(const cplx* __restrict__
 // MINB = CTAs per SM the register allocation is held to (the kernel is bound by the latency of its dependent loads: warps in
 // flight matter more than look-ahead depth -- two rows of look-ahead at 114 registers measured 0.48 ms, one row at 64 registers
 // 0.29 ms for 4 candidates at n = 1M)
-template <int CB, int SP_U, int MINB>
+// ONECHUNK: the host knows that no row has more than SP_LANES * SP_U entries (max_row_len, found when the CSR is built): the
+// loop over further chunks is compiled out.  The kernel is bound by instruction issue + latency at ~0.55 IPC per sub-partition
+// (ncu, round 2b: 171 instructions per row with the chunk loop in place and 0.30 ms at n = 1M, 4 candidates; 132 and 0.21 ms
+// without it -- profiles/microbench/spmm_ablate.cu)
+template <int CB, int SP_U, int MINB, bool ONECHUNK = false>
 __global__ void __launch_bounds__(SP_NT, MINB) csr_spmm_packed_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx,
                                                                 const cplx* __restrict__ vals, const cplx* __restrict__ P,
                                                                 long long p_gstride, cplx* __restrict__ Y, long long ldy,
@@ -133,13 +137,14 @@ __global__ void __launch_bounds__(SP_NT, MINB) csr_spmm_packed_kernel(const long
 #pragma unroll
         for (int u = 0; u < SP_U; ++u) cfma(acc, a[u], v[u]);
         // rows with more than SP_LANES * SP_U entries: the remaining chunks, same order as before, not pipelined
-        for (long long kb = kc0 + SP_LANES * SP_U; kb < kc1; kb += SP_LANES * SP_U) {
-            load_entries(kb, kc1, a, j);
+        if (!ONECHUNK)
+            for (long long kb = kc0 + SP_LANES * SP_U; kb < kc1; kb += SP_LANES * SP_U) {
+                load_entries(kb, kc1, a, j);
 #pragma unroll
-            for (int u = 0; u < SP_U; ++u) v[u] = (j[u] >= 0) ? __ldg(&P[(long long)j[u] * CB + c]) : cmake(0.0, 0.0);
+                for (int u = 0; u < SP_U; ++u) v[u] = (j[u] >= 0) ? __ldg(&P[(long long)j[u] * CB + c]) : cmake(0.0, 0.0);
 #pragma unroll
-            for (int u = 0; u < SP_U; ++u) cfma(acc, a[u], v[u]);
-        }
+                for (int u = 0; u < SP_U; ++u) cfma(acc, a[u], v[u]);
+            }
 #pragma unroll
         for (int o = SP_LANES / 2; o > 0; o >>= 1) {
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o * CB);
@@ -218,11 +223,11 @@ __global__ void __launch_bounds__(SP_NT, MINB) csr_spmm_packed8_kernel(const lon
 
 // persistent-style grid for the pipelined kernel: exactly the CTAs that are resident at once (occupancy query per instantiation),
 // every lane group walks many rows
-template <int CB, int SP_U, int MINB>
+template <int CB, int SP_U, int MINB, bool ONECHUNK = false>
 static unsigned spmm_pipe_grid(long long n) {
     static int per_sm = 0;
     if (!per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_packed_kernel<CB, SP_U, MINB>, SP_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_packed_kernel<CB, SP_U, MINB, ONECHUNK>, SP_NT, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
     }
     const long long groups_per_block = SP_NT / (SP_LANES * CB);
     const long long need = (n + groups_per_block - 1) / groups_per_block;
@@ -245,20 +250,27 @@ static unsigned spmm_pipe8_grid(long long n) {
 }  // namespace
 
 cudaError_t csr_spmm_packed4(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* P, long long p_gstride,
-                             cplx* Y, long long ldy, long long n, int c0, int ctotal, int groups, cudaStream_t stream) {
+                             cplx* Y, long long ldy, long long n, int c0, int ctotal, int groups, int max_row_len, cudaStream_t stream) {
     if (groups <= 0 || n <= 0) return cudaSuccess;
     // Measured alternatives that did not beat this kernel (round 2, 4 candidates, n = 1M, 0.29 - 0.33 ms): two rows of look-ahead
     // (114 registers, 0.48 ms), 48 / 40-register builds with spills (0.49 / 0.82 ms), a shared-memory staged matrix stream with six
     // gathers in flight per lane (commit 109fb77, 0.37 ms), an L2 persisting window over the interleaved copy (commit 1638896, 0.32 - 0.51 ms).
-    // ncu: l1tex 71 % busy (data return path 58 %), L2 36 %, DRAM 32 % -- the kernel sits at ~0.7 of the L1 limit of this
-    // access pattern (one 16-byte gather per lane, values broadcast to the four candidate lanes).
+    // Round 2b (profiles/microbench/l2_gather.cu, spmm_ablate.cu): the bare L2 gather of the same 1.34 GB takes 0.096 ms, so the
+    // kernel is NOT at the L2 limit; it is bound by bytes in flight per SM x instruction issue, and compiling the chunk loop out
+    // for matrices whose rows fit one chunk is worth 0.30 -> 0.21 ms.
+    if (max_row_len > 0 && max_row_len <= SP_LANES * 3) {
+        dim3 grid(spmm_pipe_grid<4, 3, 4, true>(n), (unsigned)groups);
+        csr_spmm_packed_kernel<4, 3, 4, true><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
+        return cudaGetLastError();
+    }
     dim3 grid(spmm_pipe_grid<4, 3, 4>(n), (unsigned)groups);
     csr_spmm_packed_kernel<4, 3, 4><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, P, p_gstride, Y, ldy, n, c0, ctotal);
     return cudaGetLastError();
 }
 
 cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* vals, const cplx* V, long long ldv, cplx* Y,
-                     long long ldy, long long n, long long ncols, int C, cplx* pack_ws, cudaStream_t stream) {
+                     long long ldy, long long n, long long ncols, int C, cplx* pack_ws, int max_row_len, cudaStream_t stream) {
+    const bool one = max_row_len > 0 && max_row_len <= SP_LANES * 3;
     const long long threads = n * SP_LANES;
     const unsigned grid = (unsigned)((threads + SP_NT - 1) / SP_NT);
     const unsigned pgrid = (unsigned)((ncols + 255) / 256);
@@ -268,7 +280,8 @@ cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* val
     if (C == 1) {
         static int pipe1 = -1;               // MAUS_SPMM_PIPE1=0: the one-row-at-a-time kernel (A/B measurements)
         if (pipe1 < 0) { const char* e = getenv("MAUS_SPMM_PIPE1"); pipe1 = e ? (atoi(e) != 0) : 1; }
-        if (pipe1) csr_spmm_packed_kernel<1, 3, 4><<<dim3(spmm_pipe_grid<1, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V, 0, Y, ldy, n, 0, 1);
+        if (pipe1 && one) csr_spmm_packed_kernel<1, 3, 4, true><<<dim3(spmm_pipe_grid<1, 3, 4, true>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V, 0, Y, ldy, n, 0, 1);
+        else if (pipe1) csr_spmm_packed_kernel<1, 3, 4><<<dim3(spmm_pipe_grid<1, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V, 0, Y, ldy, n, 0, 1);
         else csr_spmm_kernel<1, 1, 8><<<grid, SP_NT, 0, stream>>>(rowptr, colidx, vals, V, ldv, Y, ldy, n, 0, 1);
         return cudaGetLastError();
     }
@@ -285,7 +298,8 @@ cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* val
     // (blockIdx.y = group); two candidates use the half-width layout
     if (C == 2) {
         spmm_pack_kernel<2><<<dim3(pgrid, 1), 256, 0, stream>>>(V, ldv, pack_ws, ncols, 0, C);
-        csr_spmm_packed_kernel<2, 3, 4><<<dim3(spmm_pipe_grid<2, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, 0, Y, ldy, n, 0, C);
+        if (one) csr_spmm_packed_kernel<2, 3, 4, true><<<dim3(spmm_pipe_grid<2, 3, 4, true>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, 0, Y, ldy, n, 0, C);
+        else csr_spmm_packed_kernel<2, 3, 4><<<dim3(spmm_pipe_grid<2, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, pack_ws, 0, Y, ldy, n, 0, C);
         return cudaGetLastError();
     }
     // full groups of 8 candidates through the 8-wide layout, the rest (<= 7) in groups of 4 behind them in the same buffer
@@ -307,13 +321,15 @@ cudaError_t csr_spmm(const long long* rowptr, const int* colidx, const cplx* val
     if (rest == 0) return cudaGetLastError();
     cplx* ws4 = pack_ws + (size_t)ncols * 8 * g8;
     if (rest == 1) {
-        csr_spmm_packed_kernel<1, 3, 4><<<dim3(spmm_pipe_grid<1, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V + (long long)(8 * g8) * ldv, 0,
-                                                                                            Y + (long long)(8 * g8) * ldy, ldy, n, 0, 1);
+        if (one) csr_spmm_packed_kernel<1, 3, 4, true><<<dim3(spmm_pipe_grid<1, 3, 4, true>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V + (long long)(8 * g8) * ldv, 0,
+                                                                                                        Y + (long long)(8 * g8) * ldy, ldy, n, 0, 1);
+        else csr_spmm_packed_kernel<1, 3, 4><<<dim3(spmm_pipe_grid<1, 3, 4>(n), 1), SP_NT, 0, stream>>>(rowptr, colidx, vals, V + (long long)(8 * g8) * ldv, 0,
+                                                                                                 Y + (long long)(8 * g8) * ldy, ldy, n, 0, 1);
         return cudaGetLastError();
     }
     const int groups = (rest + 3) / 4;
     spmm_pack_kernel<4><<<dim3(pgrid, groups), 256, 0, stream>>>(V + (long long)(8 * g8) * ldv, ldv, ws4, ncols, 0, rest);
-    return csr_spmm_packed4(rowptr, colidx, vals, ws4, ncols * 4, Y + (long long)(8 * g8) * ldy, ldy, n, 0, rest, groups, stream);
+    return csr_spmm_packed4(rowptr, colidx, vals, ws4, ncols * 4, Y + (long long)(8 * g8) * ldy, ldy, n, 0, rest, groups, max_row_len, stream);
 }
 
 // number of complex elements of the interleaved copy csr_spmm needs for C candidates
