@@ -1,7 +1,12 @@
 // Ablation of the 4-candidate packed SpMM (spmv.cu: csr_spmm_packed_kernel<4, 3, 4>) on the K5 shape: which part of the row
 // loop costs the factor 3.4 between the kernel (0.33 ms) and the bare L2 gather of the same 1.34 GB (0.096 ms, l2_gather.cu)?
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o spmm_ablate spmm_ablate.cu && ./spmm_ablate
-// n = 1M rows, exactly 21 entries per row at uniformly random columns, P[j][4] interleaved candidates.  Scratch.
+// n = 1M rows, exactly 21 entries per row at uniformly random columns (or the K5 structure from dump_k5_csr.py as argv[1]),
+// P[j][4] interleaved candidates.  Scratch.  Measured (B200, round 2b, profiles/r02/spmm_ablate_r02c.jsonl):
+//   production shape 0.213 ms | no value stream 0.166 | no reduction / store 0.214 | neither 0.148 | not pipelined, 8 CTAs/SM 0.223
+//   lean row loop k2 (107 instead of 132 instructions per row) 0.214 - 0.227 | k3 = L2 prefetch of the entries two rows ahead 0.258
+//   L2 state (P rewritten / evicted before every launch) 0.218 / 0.226 -- i.e. the loop sits on a latency floor of ~0.21 ms that
+//   neither fewer instructions nor deeper prefetch moves; the library kernel WITH its chunk loop (171 instructions) took 0.30 ms.
 #include <cstdio>
 #include <vector>
 #include <cuda_runtime.h>
@@ -127,6 +132,64 @@ __global__ void __launch_bounds__(NT, MINB) k2(const long long* __restrict__ row
         step(B, A);
     }
 }
+// production shape + L2 prefetch of the entries two rows ahead (the register prefetch one row ahead then hits L2 instead of HBM)
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB) k3(const long long* __restrict__ rowptr, const int* __restrict__ colidx, const cplx* __restrict__ vals,
+                                              const cplx* __restrict__ P, cplx* __restrict__ Y, long long n) {
+    constexpr int LPR = SUBS * CB, GPB = NT / LPR;
+    const int l = threadIdx.x % LPR, sub = l / CB, c = l % CB;
+    const long long stride = (long long)gridDim.x * GPB;
+    long long row = (long long)blockIdx.x * GPB + threadIdx.x / LPR;
+    auto load_entries = [&](long long k0, long long k1, cplx* a, int* j) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long kk = k0 + sub + u * SUBS;
+            const bool ok = kk < k1;
+            a[u] = ok ? __ldcs(&vals[kk]) : make_double2(0.0, 0.0);
+            j[u] = ok ? __ldcs(&colidx[kk]) : -1;
+        }
+    };
+    long long k0n = 0, k1n = 0, k0nn = 0, k1nn = 0;
+    cplx an[U]; int jn[U];
+    { long long k0 = 0, k1 = 0; if (row < n) { k0 = rowptr[row]; k1 = rowptr[row + 1]; } load_entries(k0, k1, an, jn); }
+    long long rown = row + stride, rown2 = row + 2 * stride;
+    if (rown < n) { k0n = rowptr[rown]; k1n = rowptr[rown + 1]; }
+    if (rown2 < n) { k0nn = rowptr[rown2]; k1nn = rowptr[rown2 + 1]; }
+    while (__any_sync(0xffffffffu, row < n)) {
+        cplx a[U]; int j[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { a[u] = an[u]; j[u] = jn[u]; }
+        cplx v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (j[u] >= 0) ? __ldg(&P[(long long)j[u] * CB + c]) : make_double2(0.0, 0.0);
+        // L2 prefetch of the entries two rows ahead: 4 lanes cover the (<= 384 B of values, <= 96 B of indices) of that row
+        if (l < 3 && k0nn + l * 8 < k1nn) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + k0nn + l * 8));
+        if (l == 3 && k0nn < k1nn) asm volatile("prefetch.global.L2 [%0];" ::"l"(colidx + k0nn));
+        const long long rown3 = rown2 + stride;
+        long long k0n3 = 0, k1n3 = 0;
+        load_entries(k0n, k1n, an, jn);
+        if (rown3 < n) { k0n3 = rowptr[rown3]; k1n3 = rowptr[rown3 + 1]; }
+        cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) cfma(acc, a[u], v[u]);
+#pragma unroll
+        for (int o = SUBS / 2; o > 0; o >>= 1) { acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o * CB); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o * CB); }
+        if (sub == 0 && row < n) Y[(long long)c * n + row] = acc;
+        row = rown; rown = rown2; rown2 = rown3; k0n = k0nn; k1n = k1nn; k0nn = k0n3; k1nn = k1n3;
+    }
+}
+template <int MINB>
+static void run3(const char* tag, const long long* rp, const int* ci, const cplx* va, const cplx* P, cplx* Y, long long n) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int per_sm = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3<MINB>, NT, 0);
+    const unsigned grid = 148u * per_sm;
+    for (int r = 0; r < 3; ++r) k3<MINB><<<grid, NT>>>(rp, ci, va, P, Y, n);
+    cudaEventRecord(e0);
+    for (int r = 0; r < 10; ++r) k3<MINB><<<grid, NT>>>(rp, ci, va, P, Y, n);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 10;
+    printf("{\"variant\": \"%s\", \"ctas_per_sm\": %d, \"ms\": %.4f}\n", tag, per_sm, ms);
+}
 template <int MINB>
 static void run2(const char* tag, const long long* rp, const int* ci, const cplx* va, const cplx* P, cplx* Y, long long n) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -188,6 +251,8 @@ int main(int argc, char** argv) {
     run<true, true, false, 8>("not pipelined, 8 CTAs/SM", d_rp, d_ci, d_va, d_P, d_Y, n, 0);
     run<false, false, false, 8>("not pipelined, no values, no reduction, 8 CTAs/SM", d_rp, d_ci, d_va, d_P, d_Y, n, 0);
     run<true, true, true, 2>("production shape, register cap lifted (2 CTAs/SM)", d_rp, d_ci, d_va, d_P, d_Y, n, 0);
+    run3<4>("production shape + L2 prefetch two rows ahead (k3), 4 CTAs/SM", d_rp, d_ci, d_va, d_P, d_Y, n);
+    run3<3>("k3, 3 CTAs/SM", d_rp, d_ci, d_va, d_P, d_Y, n);
     run2<4>("lean row loop (k2), 4 CTAs/SM", d_rp, d_ci, d_va, d_P, d_Y, n);
     run2<5>("lean row loop (k2), 5 CTAs/SM", d_rp, d_ci, d_va, d_P, d_Y, n);
     run2<6>("lean row loop (k2), 6 CTAs/SM", d_rp, d_ci, d_va, d_P, d_Y, n);
