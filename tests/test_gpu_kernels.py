@@ -93,6 +93,28 @@ def test_lu_zero_pivot_and_nonfinite_status(eng):
     assert st[0] == _abi.ST_NONFINITE
 
 
+def test_cluster_backsolve_small_batch_statuses_and_ragged_order(eng):
+    """Batches that leave SMs idle use a cluster of CTAs per candidate for the back substitution (block-cyclic rows, x blocks
+    through DSMEM): ragged order (last block of 13 rows), several candidates, per-candidate status words."""
+    from adaptive_matrix_solver_b200 import _abi
+    n, C = 333, 3
+    rng = np.random.default_rng(21)
+    A = crand(rng, n, n) / np.sqrt(n) + np.diag(np.linspace(-2, 2, n) + 1j * np.linspace(-1, 1, n))
+    RHS = crand(rng, C, n)
+    RHS[1, 17] = np.nan                               # candidate 1 only: non-finite solution
+    sigma = np.array([0.1 + 0.2j, -0.3j, 0.7], dtype=complex)
+    eng.set_matrix(A)
+    X, st, _ = eng.solve_shifted(sigma, np.zeros(C), rng_key=None, RHS=RHS)
+    assert st[0] == 0 and st[2] == 0 and st[1] == _abi.ST_NONFINITE
+    for c in (0, 2):
+        xr = np.linalg.solve(A - sigma[c] * np.eye(n), RHS[c])
+        assert np.linalg.norm(X[c] - xr) <= 1e-11 * np.linalg.norm(xr)
+    A2 = A.copy(); A2[:, 200] = 0.0                   # exactly singular -> zero pivot reported through the cluster kernel too
+    eng.set_matrix(A2)
+    X, st, _ = eng.solve_shifted([0j], [0.0], rng_key=None, RHS=crand(rng, 1, n))
+    assert st[0] == _abi.ST_ZERO_PIVOT
+
+
 @pytest.mark.parametrize("n,C", [(8, 1), (100, 3), (256, 9), (1000, 12), (512, 64)])
 def test_rq_and_residual_match_oracle(eng, n, C):
     rng = np.random.default_rng(n + C)
