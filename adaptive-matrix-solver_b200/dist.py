@@ -146,6 +146,10 @@ def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, e
     views = getattr(shard, "_views", None)
     if views is None:
         views = shard._views = {}
+        hooks = getattr(engine, "_close_hooks", None)
+        if hooks is not None:
+            # the page-locked gather buffers die with the engine: every candidate still looking into one gets its own copy first
+            hooks.append(lambda: _detach_views(shard))
     if views:
         live_ids = {id(c) for c in live}
         for key in [k for k in views if k not in live_ids]:
@@ -189,6 +193,17 @@ def step_population_sharded(candidates, M, b, strat_params, problem_knowledge, e
         views.pop(id(c), None)               # stepped here: the vector is this rank's own array again
     _resync_host_rng(gathered, counts)
     return len(live)
+
+
+def _detach_views(shard):
+    """give every candidate whose vector is a view into a recycled gather buffer its own copy (engine shutdown)"""
+    views = getattr(shard, "_views", None) or {}
+    for c in list(views.values()):
+        if getattr(c, "v_k", None) is not None and c.v_k.base is not None:
+            c.v_k = np.array(c.v_k, copy=True)
+        if getattr(c, "x_k", None) is not None and c.x_k.base is not None:
+            c.x_k = np.array(c.x_k, copy=True)
+    views.clear()
 
 
 def _resync_host_rng(gathered, counts):

@@ -44,6 +44,7 @@ class MausEngine:
         self.matrix_epoch = [0, 0]          # uploads per slot; population._MatrixCache compares it (shared-engine safety)
         self.rowshard = None                # RowShardedOperator of this context (rowshard.py), set by enable_row_sharding
         self._pinned = []
+        self._close_hooks = []              # callables run before the page-locked buffers are released (dist.py: detach views)
         if workspace_limit_bytes:
             self._check(self._lib.maus_set_workspace_limit(self._h, int(workspace_limit_bytes)))
 
@@ -55,6 +56,9 @@ class MausEngine:
 
     def close(self):
         if getattr(self, "_h", None):
+            for hook in getattr(self, "_close_hooks", []):
+                hook()
+            self._close_hooks = []
             for p in self._pinned:
                 self._lib.maus_free_pinned(p)
             self._pinned = []
