@@ -130,3 +130,91 @@ def test_replicas_stay_identical_after_a_forced_failure(tmp_path):
     for k in ("V", "lam", "stuck", "state", "resets", "draws"):
         assert np.array_equal(r0[k], r1[k]), k
     assert r0["stuck"][1] == gens and r0["state"][1] == 3          # STUCK, counted once per generation
+
+
+class _RecycledGather:
+    """gloo stand-in of RowShardedOperator.gather: with ``pinned=True`` the result lands in one of two buffers that are reused
+    alternately -- exactly the ownership rule the sharded step has to live with on the GPU path"""
+
+    def __init__(self, world):
+        self.world = world
+        self._bufs = None
+        self._turn = 0
+        self.calls = 0
+
+    def gather(self, send, pinned=False):
+        import torch
+        import torch.distributed as dist
+        send = np.ascontiguousarray(send, dtype=np.float64).ravel()
+        parts = [torch.empty(send.size, dtype=torch.float64) for _ in range(self.world)]
+        dist.all_gather(parts, torch.from_numpy(send.copy()))
+        if not pinned:
+            return np.stack([p.numpy() for p in parts])
+        if self._bufs is None or self._bufs[0].shape[1] < send.size:
+            self._bufs = [np.full((self.world, send.size), np.nan) for _ in range(2)]
+        out = self._bufs[self._turn][:, :send.size]
+        self._turn ^= 1
+        self.calls += 1
+        for r in range(self.world):
+            out[r] = parts[r].numpy()
+        return out
+
+
+def _worker_views(rank, world, port, out_dir, n, C, gens):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from adaptive_matrix_solver_b200.dist import Shard, step_population_sharded
+    from adaptive_matrix_solver_b200.workloads import k2_matrix
+    from fake_engine import FakeEngine
+    from mock_candidate import MockCandidate, ProblemType
+    A = k2_matrix(n, seed=3)
+    np.random.seed(1); random.seed(1)
+    MockCandidate._next_id = 0
+    cands = [MockCandidate(A, ProblemType.EIGENVALUE, n) for _ in range(C)]
+    strat = dict(overall_psi_aggression_factor=1.0, max_psi_retries=25, current_convergence_threshold=1e-10)
+    know = dict(local_solver_preference="direct_solve", is_sparse_problem=False, is_hermitian=False)
+    eng = FakeEngine()
+    eng.rowshard = _RecycledGather(world)
+    eng._close_hooks = []
+    shard = Shard(rank, world, None, engine=eng)
+    step_population_sharded(cands, A, None, strat, know, eng, shard)
+    step_population_sharded(cands, A, None, strat, know, eng, shard)
+    # "host logic" (the reference's _manage_candidates) retires candidate 3 on every replica between two generations; on the
+    # rank that does not own it, its vector is a view into a recycled gather buffer at this moment
+    victim = cands[3]
+    victim.state = MockCandidate.State.RETIRED
+    frozen = victim.v_k.copy()
+    was_view = victim.v_k.base is not None
+    for g in range(gens):
+        step_population_sharded(cands, A, None, strat, know, eng, shard)
+    kept = bool(np.array_equal(victim.v_k, frozen))
+    own_after = victim.v_k.base is None
+    views_before_close = sum(1 for c in cands if c.v_k.base is not None)
+    snapshot = np.stack([c.v_k.copy() for c in cands])
+    for hook in eng._close_hooks:
+        hook()
+    for b in eng.rowshard._bufs:
+        b[:] = np.nan                                        # "the engine released its page-locked memory"
+    intact = bool(np.array_equal(np.stack([c.v_k for c in cands]), snapshot))
+    np.savez(os.path.join(out_dir, f"v{rank}.npz"), V=snapshot, kept=kept, own_after=own_after, was_view=was_view,
+             views_before_close=views_before_close, intact=intact, gathers=eng.rowshard.calls,
+             views_after=sum(1 for c in cands if c.v_k.base is not None))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_recycled_gather_buffers_never_overwrite_a_kept_vector(tmp_path):
+    """The GPU path gathers into two recycled page-locked buffers and hands out views: a candidate that leaves the live set through
+    host logic must keep its vector over later generations, and every view must be detached before the engine frees the buffers."""
+    import torch.multiprocessing as mp
+    n, C, gens = 24, 7, 4
+    port = _free_port()
+    mp.spawn(_worker_views, args=(2, port, str(tmp_path), n, C, gens), nprocs=2, join=True)
+    r0 = np.load(tmp_path / "v0.npz"); r1 = np.load(tmp_path / "v1.npz")
+    assert np.array_equal(r0["V"], r1["V"])                  # replicas agree
+    assert bool(r0["was_view"]) != bool(r1["was_view"])      # exactly one rank held the victim as a view
+    for r in (r0, r1):
+        assert bool(r["kept"]) and bool(r["own_after"]) and bool(r["intact"])
+        assert int(r["gathers"]) == 2 + gens and int(r["views_before_close"]) > 0 and int(r["views_after"]) == 0
