@@ -302,3 +302,62 @@ def test_two_rank_nccl_rowshard_matches_scipy(tmp_path):
         assert abs(parts[0]["resid"][c] - r) <= 1e-10 * r
     assert np.array_equal(parts[0]["G"], np.array([[0.0] * 5, [1.0] * 5])) and np.array_equal(parts[0]["G"], parts[1]["G"])
     assert bool(parts[0]["peer_memory"]) and bool(parts[1]["peer_memory"])
+
+
+def _nccl_sharded_worker(rank, world, port, out_dir, n, C, gens):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    import random
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # only carries the 128-byte NCCL id
+    import adaptive_matrix_solver_b200 as pkg
+    from adaptive_matrix_solver_b200.dist import Shard, step_population_sharded
+    from adaptive_matrix_solver_b200.workloads import k2_matrix
+    from mock_candidate import MockCandidate, ProblemType
+    A = k2_matrix(n, seed=3)
+    np.random.seed(1); random.seed(1)
+    MockCandidate._next_id = 0
+    cands = [MockCandidate(A, ProblemType.EIGENVALUE, n) for _ in range(C)]
+    strat = dict(overall_psi_aggression_factor=1.0, max_psi_retries=25, current_convergence_threshold=1e-10)
+    know = dict(local_solver_preference="direct_solve", is_sparse_problem=False, is_hermitian=False)
+    eng_ = pkg.MausEngine(rank)
+    eng_.enable_row_sharding(rank, world)             # communicator of the context: the exchange runs through maus_gather
+    shard = Shard(rank, world, None, engine=eng_)
+    step_population_sharded(cands, A, None, strat, know, eng_, shard)
+    step_population_sharded(cands, A, None, strat, know, eng_, shard)
+    victim = cands[3]
+    victim.state = MockCandidate.State.RETIRED        # "host logic" removes it from the live set on every replica
+    frozen = victim.v_k.copy()
+    was_view = victim.v_k.base is not None
+    for _ in range(gens):
+        step_population_sharded(cands, A, None, strat, know, eng_, shard)
+    kept = bool(np.array_equal(victim.v_k, frozen))
+    views = sum(1 for c in cands if c.v_k.base is not None)
+    snapshot = np.stack([c.v_k.copy() for c in cands])
+    resid = np.array([c.residual_k for c in cands])
+    dist.barrier()
+    eng_.close()                                      # releases the page-locked gather buffers: views must have been detached
+    intact = bool(np.array_equal(np.stack([c.v_k for c in cands]), snapshot))
+    np.savez(os.path.join(out_dir, f"sh{rank}.npz"), V=snapshot, resid=resid, kept=kept, was_view=was_view, views=views, intact=intact,
+             views_after=sum(1 for c in cands if c.v_k.base is not None))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_two_rank_nccl_sharded_step_recycles_pinned_gather_buffers(tmp_path):
+    """step_population_sharded over maus_gather: records + vectors land in two recycled page-locked buffers; replicas stay bit-identical,
+    a candidate retired by host logic keeps its vector, and nothing dangles after the engine is closed."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    n, C, gens, world = 192, 9, 4, 2
+    mp.spawn(_nccl_sharded_worker, args=(world, _free_port(), str(tmp_path), n, C, gens), nprocs=world, join=True)
+    p0, p1 = (np.load(tmp_path / f"sh{r}.npz") for r in range(world))
+    assert np.array_equal(p0["V"], p1["V"]) and np.array_equal(p0["resid"], p1["resid"])
+    assert bool(p0["was_view"]) != bool(p1["was_view"])
+    for p in (p0, p1):
+        assert bool(p["kept"]) and bool(p["intact"]) and int(p["views"]) > 0 and int(p["views_after"]) == 0
