@@ -9,13 +9,15 @@
 // Per panel (width 128):
 //   lu_panel        one thread-block CLUSTER per candidate (up to 8 CTAs x 512 threads); every thread owns one or
 //                   two rows of the panel and keeps a 16 (8) column inner block of them in registers.  Pivot search
-//                   (BLAS izamax metric |re|+|im|, first maximum) = warp shuffle -> CTA -> cluster reduction through
-//                   distributed shared memory, one cluster barrier per column.  Pivoting is IMPLICIT inside the
+//                   (BLAS izamax metric |re|+|im|, first maximum) = REDUX on integer keys inside a warp -> CTA -> the
+//                   CTAs' records exchanged with st.async into every CTA's shared memory, completing transaction bytes
+//                   on the receivers' mbarriers (no cluster barrier in the column loop).  Pivoting is IMPLICIT inside the
 //                   panel (rows are marked, not moved); the net permutation is emitted as <= 256 (dst, src) pairs.
 //   lu_permute_rows applies those pairs to every column >= the outer block's first column in one parallel pass (no
 //                   sequential swap chain).
 //   lu_trtri        inverse of the unit-lower 128 x 128 diagonal block, so that the triangular solve for U12 and the
 //                   trailing update are both plain GEMMs on the FP64 tensor pipe (zgemm.cu).
+// After the last panel: lu_backsolve (one CTA per candidate) or lu_backsolve_cluster (2 - 8 CTAs per candidate, small batches).
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
