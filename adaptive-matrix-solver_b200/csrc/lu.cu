@@ -735,8 +735,9 @@ __global__ void __launch_bounds__(BS_NT) lu_backsolve_cluster_kernel(const cplx*
         }
         __syncthreads();         // the owner of block kb - 1 reads its y entries next; D is rewritten
     }
-    if (mybad) *cluster.map_shared_rank(&bad[rank], 0) = 1;
-    else if (tid == 0) *cluster.map_shared_rank(&bad[rank], 0) = 0;
+    // one flag per CTA (any lane of any owned block saw a non-finite x), collected by rank 0
+    const int cta_bad = __syncthreads_or(mybad);
+    if (tid == 0) *cluster.map_shared_rank(&bad[rank], 0) = cta_bad ? 1 : 0;
     cluster.sync();
     if (rank == 0 && tid == 0) {
         int any = 0;
